@@ -1,0 +1,138 @@
+/*
+ * b200pc.h -- C ABI of libb200pc.so: the B200-native (sm_100a) geometric hot path behind
+ * PointINet / PolyPCI / FlowNet3D-style models of jlx-dxl/Point-Cloud-Interpolation-.
+ *
+ * The reference has NO native interface: its hot path is plain Python functions imported by
+ * name (Utils/Layers.py:8-10, Utils/Utils.py:9, PolyPCI/Models/Models_V1.py:12).  Each entry
+ * point below states which reference function (file:line, relative to the reference root) it
+ * replaces; the Python facade `b200pc` binds them 1:1 under the reference's own names
+ * (see INTEGRATION.md for the binding a maintainer adds).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the function name ends in _host;
+ *  - fp32 tensors are C-contiguous, point-major: xyz [B,N,3], features [B,N,C];
+ *  - indices are int64 (torch.long), exactly as the reference produces/consumes them;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *    stream-ordered, nothing synchronises, no global mutable state, re-entrant;
+ *  - `workspace` is caller-owned device scratch of at least *_workspace_bytes(); it may be
+ *    reused by the next call on the same stream;
+ *  - return value: 0 on success, a negative B200PC_E* code on failure; the message is
+ *    available from b200pc_last_error() (thread-local).  Nothing throws across this ABI.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry returns
+ *    B200PC_ECUDA.
+ */
+#ifndef B200PC_H
+#define B200PC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PC_OK        0
+#define B200PC_EINVAL   -1 /* bad argument (k > N, null pointer, ...) */
+#define B200PC_ECUDA    -2 /* CUDA runtime error (launch failure, no device, ...) */
+#define B200PC_EWORKSPACE -3 /* workspace too small */
+
+/* distance arithmetic ("form"): which fp32 rounding sequence a search reproduces */
+#define B200PC_FORM_REF_NORM_FIRST 0 /* square_distance(refs, queries): kNN site Utils/Layers.py:51 */
+#define B200PC_FORM_QRY_NORM_FIRST 1 /* square_distance(queries, refs): Utils/Pointnet2Utils.py:102, Utils/Layers.py:180 */
+#define B200PC_FORM_DIRECT         2 /* sum((q-r)^2) with FMA accumulation: pytorch3d.ops.knn_points */
+
+typedef void *b200pc_stream_t;
+
+const char *b200pc_last_error(void);
+int b200pc_version(void);
+/* number of SMs of the current device, or a negative error code */
+int b200pc_device_sm_count(void);
+
+/* ---- scratch sizing -------------------------------------------------------------------- */
+/* scratch for any neighbour search (knn / ball_query / three_nn / chamfer) of S queries
+ * against N refs per batch item with lists of length k (k = nsample for the ball query). */
+size_t b200pc_search_workspace_bytes(int B, int N, int S, int k);
+size_t b200pc_fps_workspace_bytes(int B, int N);
+
+/* ---- a1: square_distance(src, dst)  Utils/Pointnet2Utils.py:20-41 ---------------------- */
+/* out[b,n,m] = ((-2*dot(src_n,dst_m)) + |src_n|^2) + |dst_m|^2, bit-identical to torch CPU. */
+int b200pc_square_distance(const float *src, const float *dst, int B, int N, int M, float *out,
+                           b200pc_stream_t stream);
+
+/* ---- a4 / a8: k nearest refs for each query --------------------------------------------- */
+/* form 0  -> Group.forward kNN branch, Utils/Layers.py:50-53 (exposed as knn_point)
+ * form 2  -> pytorch3d.ops.knn_points(p1=qry, p2=ref, K=k) as called at Utils/Layers.py:220,
+ *            311,393,430; PolyPCI/Models/Models_V1.py:113; PointINet20230424/models/layers.py:360
+ * idx [B,S,k] int64 ascending by (distance, index); dist [B,S,k] may be NULL.               */
+int b200pc_knn(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
+               float *dist, void *workspace, size_t workspace_bytes, b200pc_stream_t stream);
+
+/* ---- a2: query_ball_point(radius, nsample, xyz, new_xyz)  Utils/Pointnet2Utils.py:88-108 -- */
+/* r2 = (float)(radius*radius) computed in double by the caller.  idx [B,S,nsample] int64:
+ * the nsample lowest-index refs with NOT(d > r2), padded with the first; N if the ball is empty. */
+int b200pc_ball_query(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
+                      int64_t *idx, void *workspace, size_t workspace_bytes, b200pc_stream_t stream);
+
+/* ---- a5: three_nn + weights  Utils/Layers.py:180-186 / Utils/Pointnet2Utils.py:297-303 ---- */
+/* unknown [B,N,3] dense queries, known [B,S,3] sparse refs (S >= 3).
+ * dist [B,N,3] (ascending, raw expanded-form values), idx [B,N,3] int64, weight [B,N,3] or NULL.
+ * variant 0: d<1e-10 -> 1e-10, w=(1/d)/sum ; variant 1: w = 1/(d+1e-8) normalised.            */
+int b200pc_three_nn(const float *unknown, const float *known, int B, int N, int S, int variant, float *dist,
+                    int64_t *idx, float *weight, void *workspace, size_t workspace_bytes,
+                    b200pc_stream_t stream);
+
+/* ---- a5: three_interpolate  Utils/Layers.py:187-188 / Utils/Pointnet2Utils.py:304 -------- */
+/* feat [B,S,C], idx [B,N,3], weight [B,N,3] -> out [B,N,C] = (f0*w0 + f1*w1) + f2*w2         */
+int b200pc_three_interpolate(const float *feat, const int64_t *idx, const float *weight, int B, int S, int N,
+                             int C, float *out, b200pc_stream_t stream);
+/* gradients: gfeat [B,S,C] must be zero-filled by the caller (atomic accumulation);
+ * gweight [B,N,3] may be NULL. */
+int b200pc_three_interpolate_bwd(const float *gout, const float *feat, const int64_t *idx, const float *weight,
+                                 int B, int S, int N, int C, float *gfeat, float *gweight,
+                                 b200pc_stream_t stream);
+
+/* ---- a3: farthest_point_sample(xyz, npoint)  Utils/Pointnet2Utils.py:64-85 --------------- */
+/* start [B] int64: the first centroid of each cloud (the facade draws it with torch.randint
+ * on the CPU generator exactly as the reference does).  idx [B,npoint] int64.                */
+int b200pc_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, void *workspace,
+               size_t workspace_bytes, b200pc_stream_t stream);
+
+/* ---- a6: index_points(points, idx)  Utils/Pointnet2Utils.py:44-61 ------------------------ */
+/* points [B,N,C]; idx flattened to [B,R] (R = prod(idx.shape[1:])); out [B,R,C].
+ * Negative indices wrap once (python semantics).  If oob_flag != NULL, *oob_flag (device int,
+ * zero-initialised by the caller) is set to 1 when an index is out of range; such rows are
+ * written as zeros.  The facade turns the flag into IndexError like the reference.           */
+int b200pc_gather(const float *points, const int64_t *idx, int B, int N, int C, int64_t R, float *out,
+                  int *oob_flag, b200pc_stream_t stream);
+/* gpoints [B,N,C] must be zero-filled by the caller: gpoints[b, idx[b,r], :] += gout[b,r,:]  */
+int b200pc_gather_bwd(const float *gout, const int64_t *idx, int B, int N, int C, int64_t R, float *gpoints,
+                      b200pc_stream_t stream);
+
+/* ---- a9: chamfer_loss  Utils/Utils.py:39-48 -> pytorch3d.loss.chamfer_distance defaults --- */
+/* x [B,N,3], y [B,M,3].  Outputs: per-point nearest squared distance and index in both
+ * directions (dx,ix: [B,N]; dy,iy: [B,M]) and the scalar loss[1] =
+ * mean_b( mean_i dx + mean_j dy ).  loss is written (not accumulated).                       */
+int b200pc_chamfer_fwd(const float *x, const float *y, int B, int N, int M, float *dx, int64_t *ix, float *dy,
+                       int64_t *iy, float *loss, void *workspace, size_t workspace_bytes,
+                       b200pc_stream_t stream);
+/* gx [B,N,3], gy [B,M,3] are written (zero-filled internally); gloss is a device scalar.     */
+int b200pc_chamfer_bwd(const float *x, const float *y, const int64_t *ix, const int64_t *iy, const float *gloss,
+                       int B, int N, int M, float *gx, float *gy, b200pc_stream_t stream);
+
+/* ---- measurement helper: sustained FP32 FMA throughput of the current device ------------- */
+/* runs a register-resident FFMA2 chain kernel for `iters` iterations; *tflops receives the
+ * measured rate (2 FLOP per FMA).  Used by bench.py for the FP32 roofline denominator.       */
+int b200pc_fma_peak(int iters, double *tflops, double *ms, b200pc_stream_t stream);
+
+/* ---- host-buffer convenience wrappers (non-torch callers) -------------------------------- */
+/* Same semantics as above with HOST pointers: allocate, copy in, run, copy out, synchronise. */
+int b200pc_knn_host(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
+                    float *dist);
+int b200pc_ball_query_host(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
+                           int64_t *idx);
+int b200pc_fps_host(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PC_H */

@@ -1,0 +1,74 @@
+"""The reference's geometric primitives under their own names, signatures and tensor layouts.
+
+Mirrors the module-level functions of the reference's Utils/Pointnet2Utils.py (== PolyPCI/Utils/
+Pointnet2Utils.py, ~= PointINet20230424/models/pointnet2_utils.py) so that Utils/Layers.py,
+Models/*.py, train*.py and test.py can import them unmodified (see dropin.py), plus the three
+names north_star asks for that exist in the reference only as inline code:
+
+  knn_point(nsample, xyz, new_xyz)        <- Group.forward kNN branch, Utils/Layers.py:50-53
+  three_nn(unknown, known)                <- Utils/Layers.py:180-182, Utils/Pointnet2Utils.py:297-299
+  three_interpolate(feats, idx, weight)   <- Utils/Layers.py:187-188, Utils/Pointnet2Utils.py:304
+
+Every function runs a hand-written sm_100a kernel from libb200pc.so; none has a CPU path.
+"""
+import torch
+
+from . import ops
+
+
+def square_distance(src, dst):
+    """Utils/Pointnet2Utils.py:20-41.  src [B,N,C=3], dst [B,M,3] -> [B,N,M].
+    Bit-identical to the reference's torch-CPU result: ((-2*src.dst) + |src|^2) + |dst|^2."""
+    return ops.square_distance(src, dst)
+
+
+def index_points(points, idx):
+    """Utils/Pointnet2Utils.py:44-61.  points [B,N,C], idx [B,S] or [B,S,K] (any integer dtype)
+    -> [B,S,C] / [B,S,K,C].  Negative indices wrap; out-of-range raises IndexError when
+    b200pc.ops.CHECK_BOUNDS is on (off by default: it costs a host sync)."""
+    return ops.gather(points, idx)
+
+
+def farthest_point_sample(xyz, npoint):
+    """Utils/Pointnet2Utils.py:64-85.  xyz [B,N,3] -> [B,npoint] int64.
+    Like the reference (:76) the first centroid is drawn with torch.randint(0, N, (B,)) from
+    the CPU default generator, so torch.manual_seed() reproduces the reference's samples."""
+    B, N, _ = xyz.shape
+    start = torch.randint(0, N, (B,), dtype=torch.long)
+    return ops.fps(xyz, npoint, start.to(xyz.device, non_blocking=True))
+
+
+def farthest_point_sample_from(xyz, npoint, start):
+    """same, with caller-provided first centroids `start` [B] (no RNG draw)."""
+    return ops.fps(xyz, npoint, start)
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """Utils/Pointnet2Utils.py:88-108.  xyz [B,N,3] refs, new_xyz [B,S,3] queries ->
+    [B,S,nsample] int64: lowest-index neighbours within the radius, padded with the first one;
+    a query whose ball is empty gets N in every slot (the reference's sentinel, never clamped)."""
+    return ops.ball_query(radius, nsample, xyz, new_xyz)
+
+
+def knn_point(nsample, xyz, new_xyz):
+    """kNN as Group.forward computes it (Utils/Layers.py:50-53): xyz [B,N,3] refs, new_xyz
+    [B,S,3] queries -> [B,S,nsample] int64 ascending by (distance, index)."""
+    return ops.knn_search(xyz, new_xyz, nsample, ops.FORM_REF_NORM_FIRST)
+
+
+def three_nn(unknown, known):
+    """unknown [B,N,3], known [B,S,3] -> (dist [B,N,3], idx [B,N,3] int64), the three nearest
+    known points in ascending order; dist are the reference's expanded-form squared distances."""
+    dist, idx, _ = ops.three_nn(unknown, known, variant=0, want_weight=False)
+    return dist, idx
+
+
+def three_nn_weights(unknown, known, variant=0):
+    """three_nn plus the inverse-distance weights.  variant 0 = FeaturePropagation
+    (Utils/Layers.py:183-186), variant 1 = PointNetFeaturePropagation (Utils/Pointnet2Utils.py:301-303)."""
+    return ops.three_nn(unknown, known, variant=variant, want_weight=True)
+
+
+def three_interpolate(feats, idx, weight):
+    """feats [B,S,C], idx [B,N,3], weight [B,N,3] -> [B,N,C]; differentiable in feats and weight."""
+    return ops.three_interpolate(feats, idx, weight)

@@ -1,0 +1,134 @@
+// common.cuh -- shared plumbing for libb200pc.so (sm_100a only).
+//   * error handling behind the C ABI (thread-local message, no exceptions cross the ABI)
+//   * PTX wrappers: packed fp32x2 math (FFMA2/FMUL2/FADD2), 3-input min (FMNMX3),
+//     mbarrier, 1-D bulk TMA copy (cp.async.bulk -> UBLKCP), vector reductions
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200pc.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb200pc is written for sm_100a (B200) only"
+#endif
+
+namespace b200pc {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define B200PC_CUDA(call)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) return ::b200pc::cuda_fail(_e, #call, __FILE__, __LINE__);     \
+    } while (0)
+
+#define B200PC_REQUIRE(cond, ...)                                                             \
+    do {                                                                                      \
+        if (!(cond)) { ::b200pc::set_error(__VA_ARGS__); return B200PC_EINVAL; }              \
+    } while (0)
+
+#define B200PC_LAUNCH_CHECK() B200PC_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(b200pc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic.  A "pair" is a 64-bit register holding two IEEE fp32 lanes; each op
+// rounds both lanes to nearest-even independently, exactly like the scalar instruction would.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA 1-D).  Addresses are 32-bit shared-window addresses.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming (no L1 allocate) 128-bit global accesses for the HBM-bound kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, const float4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *p, const float4 &v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace b200pc

@@ -1,0 +1,197 @@
+// fps.cu -- farthest_point_sample (Utils/Pointnet2Utils.py:64-85 in the reference), sm_100a.
+//
+// npoint strictly sequential rounds; each round updates a running min-distance for every point
+// and picks the FIRST arg-max.  The reference spends ~8 ATen launches per round; here one
+// thread-block CLUSTER owns one cloud for the whole loop:
+//   * every thread keeps P points (x,y,z,min-dist) in REGISTERS for all rounds; 512 threads x
+//     P<=16 = 8192 points per CTA, up to 16 CTAs per cluster (131072 points);
+//   * the update is packed fp32x2 math in the reference's exact rounding order
+//     d = ((dx*dx + dy*dy) + dz*dz), dx = x - cx, no FMA;
+//   * arg-max: min-dists are >= +0, so their bit patterns order like unsigned ints:
+//     REDUX.MAX per warp, one __syncthreads, REDUX again over the warp maxima; only the threads
+//     that hold the block maximum resolve the lowest index (shared atomicMin);
+//   * across CTAs: each CTA stores {max bits, index, centroid xyz} into every peer's shared
+//     memory (DSMEM), one cluster barrier per round, every thread then picks the winner locally.
+// HBM traffic is N*12 bytes in and npoint*8 bytes out per cloud; the kernel is bound by the
+// barrier latency of a round, reported by bench.py as microseconds per round.
+#include <cooperative_groups.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace b200pc {
+
+constexpr int FPS_T = 512;        // threads per CTA
+constexpr int FPS_WARPS = FPS_T / 32;
+constexpr int FPS_MAX_CLUSTER = 16;
+
+struct FpsRecord {  // what a CTA tells its peers each round
+    unsigned int bits;  // float bits of the CTA-wide max of min-dist
+    int idx;            // lowest point index attaining it
+    float x, y, z;      // its coordinates
+    int pad[3];
+};
+
+template <int P>
+__global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xyz, int N, int npoint,
+                                                    const int64_t *__restrict__ start, int64_t *__restrict__ out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cta_base = rank * (FPS_T * P);
+
+    extern __shared__ __align__(16) float fps_smem[];
+    float *sx = fps_smem, *sy = sx + FPS_T * P, *sz = sy + FPS_T * P;
+    __shared__ unsigned int warp_max[FPS_WARPS];
+    __shared__ int cand[2];
+    __shared__ FpsRecord rec[2][FPS_MAX_CLUSTER];
+
+    const float *cloud = xyz + (size_t)b * N * 3;
+    float x[P], y[P], z[P], mind[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int i = cta_base + p * FPS_T + t;
+        if (i < N) {
+            x[p] = cloud[i * 3 + 0]; y[p] = cloud[i * 3 + 1]; z[p] = cloud[i * 3 + 2];
+            mind[p] = 1e10f;
+        } else {  // padding: min-dist 0 loses every tie because its index is larger than any real one
+            x[p] = 0.f; y[p] = 0.f; z[p] = 0.f; mind[p] = 0.f;
+        }
+        sx[p * FPS_T + t] = x[p]; sy[p * FPS_T + t] = y[p]; sz[p * FPS_T + t] = z[p];
+    }
+    if (t == 0) { cand[0] = INT_MAX; cand[1] = INT_MAX; }
+    int far = (int)start[b];
+    float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
+    if (C > 1) cluster.sync(); else __syncthreads();
+
+    for (int it = 0; it < npoint; ++it) {
+        if (rank == 0 && t == 0) out[(size_t)b * npoint + it] = far;
+        if (it == npoint - 1) break;  // the last pick needs no further update
+
+        // ---- running-min update, reference rounding order, two points per instruction ----
+        float lmax = 0.f;
+        if (P >= 2) {
+            const f32x2 ncx = splat2(-cx), ncy = splat2(-cy), ncz = splat2(-cz);
+#pragma unroll
+            for (int p = 0; p < P; p += 2) {
+                const f32x2 dx = add2(pack2(x[p], x[p + 1]), ncx);
+                const f32x2 dy = add2(pack2(y[p], y[p + 1]), ncy);
+                const f32x2 dz = add2(pack2(z[p], z[p + 1]), ncz);
+                const f32x2 s = add2(add2(mul2(dx, dx), mul2(dy, dy)), mul2(dz, dz));
+                float d0, d1;
+                unpack2(s, d0, d1);
+                mind[p] = fminf(mind[p], d0);
+                mind[p + 1] = fminf(mind[p + 1], d1);
+                lmax = fmaxf(lmax, fmaxf(mind[p], mind[p + 1]));
+            }
+        } else {
+            const float dx = __fadd_rn(x[0], -cx), dy = __fadd_rn(y[0], -cy), dz = __fadd_rn(z[0], -cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            mind[0] = fminf(mind[0], d);
+            lmax = mind[0];
+        }
+
+        // ---- block arg-max (first index) ----
+        const unsigned int lbits = __float_as_uint(lmax);
+        const unsigned int wbits = __reduce_max_sync(0xffffffffu, lbits);
+        if (lane == 0) warp_max[warp] = wbits;
+        __syncthreads();
+        const unsigned int cbits = __reduce_max_sync(0xffffffffu, warp_max[lane & (FPS_WARPS - 1)]);
+        if (lbits == cbits) {
+            int lp = 0;
+#pragma unroll
+            for (int p = P - 1; p >= 0; --p)
+                if (mind[p] == lmax) lp = p;
+            atomicMin(&cand[it & 1], cta_base + lp * FPS_T + t);
+        }
+        if (t == 0) cand[(it + 1) & 1] = INT_MAX;  // reset the other parity for the next round
+        __syncthreads();
+        const int ci = cand[it & 1];
+        const int cl = ci - cta_base;
+
+        if (C == 1) {
+            far = ci;
+            cx = sx[cl]; cy = sy[cl]; cz = sz[cl];
+        } else {
+            // ---- cluster arg-max: all-to-all of one 32-byte record through DSMEM ----
+            if (t < C) {
+                FpsRecord r;
+                r.bits = cbits; r.idx = ci; r.x = sx[cl]; r.y = sy[cl]; r.z = sz[cl];
+                r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                FpsRecord *peer = cluster.map_shared_rank(&rec[it & 1][rank], t);
+                *reinterpret_cast<int4 *>(peer) = *reinterpret_cast<int4 *>(&r);
+                *(reinterpret_cast<int4 *>(peer) + 1) = *(reinterpret_cast<int4 *>(&r) + 1);
+            }
+            cluster.sync();
+            unsigned int bb = 0u;
+            int bi = INT_MAX;
+            for (int r = 0; r < C; ++r) {
+                const unsigned int vb = rec[it & 1][r].bits;
+                const int vi = rec[it & 1][r].idx;
+                if (vb > bb || (vb == bb && vi < bi)) { bb = vb; bi = vi; cx = rec[it & 1][r].x; cy = rec[it & 1][r].y; cz = rec[it & 1][r].z; }
+            }
+            far = bi;
+        }
+    }
+    if (C > 1) cluster.sync();  // nobody exits while a peer may still write into its shared memory
+}
+
+template <int P>
+static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, int C,
+                      cudaStream_t st) {
+    auto kern = fps_kernel<P>;
+    const size_t smem = (size_t)3 * FPS_T * P * sizeof(float);
+    B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, B, 1);
+    cfg.blockDim = dim3(FPS_T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    B200PC_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, idx));
+    return B200PC_OK;
+}
+
+// cluster size and points-per-thread for a cloud of N points in a batch of B
+static void fps_shape(int B, int N, int *C_out, int *P_out) {
+    const int sms = sm_count();
+    int C = 1;
+    while (C < FPS_MAX_CLUSTER && (long)C * FPS_T * 16 < N) C *= 2;          // capacity
+    while (C < 8 && (long)B * C * 2 <= sms && (long)C * FPS_T * 2 <= N) C *= 2;   // latency: spread while SMs are idle
+    int P = 1;
+    while ((long)C * FPS_T * P < N) P *= 2;
+    *C_out = C; *P_out = P;
+}
+
+}  // namespace b200pc
+
+using namespace b200pc;
+
+extern "C" size_t b200pc_fps_workspace_bytes(int, int) { return 256; }
+
+extern "C" int b200pc_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, void *,
+                          size_t, b200pc_stream_t stream) {
+    B200PC_REQUIRE(xyz && start && idx, "fps: null pointer");
+    B200PC_REQUIRE(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
+    B200PC_REQUIRE((long)N <= (long)FPS_MAX_CLUSTER * FPS_T * 16, "fps: N=%d exceeds the %d points one cluster can hold",
+                   N, FPS_MAX_CLUSTER * FPS_T * 16);
+    if (B == 0 || npoint == 0) return B200PC_OK;
+    int C, P;
+    fps_shape(B, N, &C, &P);
+    cudaStream_t st = as_stream(stream);
+    switch (P) {
+        case 1: return launch_fps<1>(xyz, B, N, npoint, start, idx, C, st);
+        case 2: return launch_fps<2>(xyz, B, N, npoint, start, idx, C, st);
+        case 4: return launch_fps<4>(xyz, B, N, npoint, start, idx, C, st);
+        case 8: return launch_fps<8>(xyz, B, N, npoint, start, idx, C, st);
+        default: return launch_fps<16>(xyz, B, N, npoint, start, idx, C, st);
+    }
+}

@@ -1,0 +1,303 @@
+// gather.cu -- HBM-bound row movers (sm_100a):
+//   index_points        Utils/Pointnet2Utils.py:44-61      (also pytorch3d knn_gather, Utils/Layers.py:396,434)
+//   three_nn weights    Utils/Layers.py:183-186 (variant 0), Utils/Pointnet2Utils.py:301-303 (variant 1)
+//   three_interpolate   Utils/Layers.py:187-188, Utils/Pointnet2Utils.py:304
+// and their gradients.  Rows are moved as 16-byte vectors whenever the channel count and the
+// base addresses allow it; loads of streamed data bypass L1 allocation, index/weight loads are
+// shared by the threads of a row through L1.  Grids are sized in whole waves of 148 SMs.
+#include "common.cuh"
+#include "search.cuh"
+
+namespace b200pc {
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int wave_grid(long work_items, int threads, int per_thread) {
+    const int sms = sm_count();
+    long blocks = (work_items + (long)threads * per_thread - 1) / ((long)threads * per_thread);
+    const long cap = (long)sms * 16;  // enough CTAs in flight to saturate HBM, then grid-stride
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------
+// index_points
+// ------------------------------------------------------------------------------------------
+// one thread per 16-byte vector of the output; 4 independent vectors in flight per thread
+template <int UNROLL>
+__global__ void __launch_bounds__(256) gather_vec4_kernel(const float4 *__restrict__ points, const int64_t *__restrict__ idx,
+                                                          int N, int C4, long R, long total, float4 *__restrict__ out,
+                                                          int *__restrict__ oob) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * UNROLL) {
+        float4 val[UNROLL];
+        bool live[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long v = v0 + u * stride;
+            live[u] = v < total;
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live[u]) {
+                const long row = v / C4;
+                const int col = (int)(v - row * C4);
+                const long b = row / R;
+                long i = idx[row];
+                if (i < 0) i += N;
+                if (i < 0 || i >= N) { if (oob) *oob = 1; }
+                else val[u] = ldg_stream(points + ((b * N + i) * C4 + col));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (live[u]) stg_stream(out + (v0 + u * stride), val[u]);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_scalar_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx,
+                                                            int N, int C, long R, long total, float *__restrict__ out,
+                                                            int *__restrict__ oob) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+        const long row = v / C;
+        const int col = (int)(v - row * C);
+        const long b = row / R;
+        long i = idx[row];
+        if (i < 0) i += N;
+        float r = 0.f;
+        if (i < 0 || i >= N) { if (oob) *oob = 1; }
+        else r = __ldg(points + ((b * N + i) * C + col));
+        out[v] = r;
+    }
+}
+
+// gradient: gpoints[b, idx[b,r], :] += gout[b,r,:]
+__global__ void __launch_bounds__(256) scatter_add_vec4_kernel(const float4 *__restrict__ gout, const int64_t *__restrict__ idx,
+                                                               int N, int C4, long R, long total, float *__restrict__ gpoints) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+        const long row = v / C4;
+        const int col = (int)(v - row * C4);
+        const long b = row / R;
+        long i = idx[row];
+        if (i < 0) i += N;
+        if (i < 0 || i >= N) continue;
+        red_add_v4(gpoints + ((b * N + i) * C4 + col) * 4, ldg_stream(gout + v));
+    }
+}
+
+__global__ void __launch_bounds__(256) scatter_add_scalar_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx,
+                                                                 int N, int C, long R, long total, float *__restrict__ gpoints) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+        const long row = v / C;
+        const int col = (int)(v - row * C);
+        const long b = row / R;
+        long i = idx[row];
+        if (i < 0) i += N;
+        if (i < 0 || i >= N) continue;
+        atomicAdd(gpoints + ((b * N + i) * C + col), gout[v]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// three-NN weights
+// ------------------------------------------------------------------------------------------
+__global__ void three_weights_kernel(const float *__restrict__ dist, long rows, int variant, float *__restrict__ w) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float inv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float d = dist[r * 3 + j];
+        if (variant == 0) {
+            if (d < 1e-10f) d = 1e-10f;        // dists[dists < 1e-10] = 1e-10
+            inv[j] = __fdiv_rn(1.0f, d);
+        } else {
+            inv[j] = __fdiv_rn(1.0f, __fadd_rn(d, 1e-8f));
+        }
+    }
+    const float norm = __fadd_rn(__fadd_rn(inv[0], inv[1]), inv[2]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[r * 3 + j] = __fdiv_rn(inv[j], norm);
+}
+
+// ------------------------------------------------------------------------------------------
+// three_interpolate: out[b,n,:] = (f[i0]*w0 + f[i1]*w1) + f[i2]*w2   (separate mul / add)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mix3(float a, float wa, float b, float wb, float c, float wc) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb)), __fmul_rn(c, wc));
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) interp_vec4_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                          const float *__restrict__ w, int S, int C4, long N, long total,
+                                                          float4 *__restrict__ out) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * UNROLL) {
+        float4 f[UNROLL][3];
+        float ww[UNROLL][3];
+        bool live[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long v = v0 + u * stride;
+            live[u] = v < total;
+            if (live[u]) {
+                const long row = v / C4;
+                const int col = (int)(v - row * C4);
+                const long b = row / N;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const long i = idx[row * 3 + j];
+                    ww[u][j] = w[row * 3 + j];
+                    f[u][j] = __ldg(feat + ((b * S + i) * C4 + col));   // sparse rows are re-read ~3N/S times: keep in L1/L2
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!live[u]) continue;
+            float4 o;
+            o.x = mix3(f[u][0].x, ww[u][0], f[u][1].x, ww[u][1], f[u][2].x, ww[u][2]);
+            o.y = mix3(f[u][0].y, ww[u][0], f[u][1].y, ww[u][1], f[u][2].y, ww[u][2]);
+            o.z = mix3(f[u][0].z, ww[u][0], f[u][1].z, ww[u][1], f[u][2].z, ww[u][2]);
+            o.w = mix3(f[u][0].w, ww[u][0], f[u][1].w, ww[u][1], f[u][2].w, ww[u][2]);
+            stg_stream(out + (v0 + u * stride), o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) interp_scalar_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                            const float *__restrict__ w, int S, int C, long N, long total,
+                                                            float *__restrict__ out) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+        const long row = v / C;
+        const int col = (int)(v - row * C);
+        const long b = row / N;
+        const long i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
+        out[v] = mix3(__ldg(feat + (b * S + i0) * C + col), w[row * 3], __ldg(feat + (b * S + i1) * C + col), w[row * 3 + 1],
+                      __ldg(feat + (b * S + i2) * C + col), w[row * 3 + 2]);
+    }
+}
+
+// gradient: one warp per dense row.  gfeat[b,i_j,:] += gout*w_j ; gweight[b,n,j] = <gout, feat[i_j]>
+__global__ void __launch_bounds__(256) interp_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ feat,
+                                                         const int64_t *__restrict__ idx, const float *__restrict__ w, int S,
+                                                         int C, long N, long rows, float *__restrict__ gfeat,
+                                                         float *__restrict__ gweight) {
+    const int lane = threadIdx.x & 31;
+    const long warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long row = warp_global; row < rows; row += nwarps) {
+        const long b = row / N;
+        long id[3];
+        float ww[3], acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { id[j] = idx[row * 3 + j]; ww[j] = w[row * 3 + j]; }
+        for (int c = lane; c < C; c += 32) {
+            const float g = gout[row * C + c];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const long o = (b * S + id[j]) * C + c;
+                atomicAdd(gfeat + o, g * ww[j]);
+                if (gweight) acc[j] += g * feat[o];
+            }
+        }
+        if (gweight) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float a = acc[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) gweight[row * 3 + j] = a;
+            }
+        }
+    }
+}
+
+}  // namespace b200pc
+
+using namespace b200pc;
+
+extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int N, int C, int64_t R, float *out,
+                             int *oob_flag, b200pc_stream_t stream) {
+    B200PC_REQUIRE(points && idx && out, "gather: null pointer");
+    B200PC_REQUIRE(B >= 0 && N >= 1 && C >= 1 && R >= 0, "gather: bad sizes");
+    if (B == 0 || R == 0) return B200PC_OK;
+    cudaStream_t st = as_stream(stream);
+    if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
+        const long total = (long)B * R * (C / 4);
+        gather_vec4_kernel<4><<<wave_grid(total, 256, 4), 256, 0, st>>>(
+            reinterpret_cast<const float4 *>(points), idx, N, C / 4, (long)R, total, reinterpret_cast<float4 *>(out), oob_flag);
+    } else {
+        const long total = (long)B * R * C;
+        gather_scalar_kernel<<<wave_grid(total, 256, 1), 256, 0, st>>>(points, idx, N, C, (long)R, total, out, oob_flag);
+    }
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}
+
+extern "C" int b200pc_gather_bwd(const float *gout, const int64_t *idx, int B, int N, int C, int64_t R, float *gpoints,
+                                 b200pc_stream_t stream) {
+    B200PC_REQUIRE(gout && idx && gpoints, "gather_bwd: null pointer");
+    if (B == 0 || R == 0) return B200PC_OK;
+    cudaStream_t st = as_stream(stream);
+    if (C % 4 == 0 && aligned16(gout) && aligned16(gpoints)) {
+        const long total = (long)B * R * (C / 4);
+        scatter_add_vec4_kernel<<<wave_grid(total, 256, 1), 256, 0, st>>>(reinterpret_cast<const float4 *>(gout), idx, N,
+                                                                          C / 4, (long)R, total, gpoints);
+    } else {
+        const long total = (long)B * R * C;
+        scatter_add_scalar_kernel<<<wave_grid(total, 256, 1), 256, 0, st>>>(gout, idx, N, C, (long)R, total, gpoints);
+    }
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}
+
+extern "C" int b200pc_three_nn(const float *unknown, const float *known, int B, int N, int S, int variant, float *dist,
+                               int64_t *idx, float *weight, void *workspace, size_t workspace_bytes,
+                               b200pc_stream_t stream) {
+    B200PC_REQUIRE(dist && idx, "three_nn: dist and idx outputs are required");
+    B200PC_REQUIRE(S >= 3, "three_nn: needs at least 3 known points, got S=%d", S);
+    B200PC_REQUIRE(variant == 0 || variant == 1, "three_nn: unknown weight variant %d", variant);
+    cudaStream_t st = as_stream(stream);
+    // refs = known (sparse), queries = unknown (dense); the dense cloud is `src` of square_distance
+    int rc = run_topk(known, unknown, B, S, N, 3, B200PC_FORM_QRY_NORM_FIRST, idx, dist, workspace, workspace_bytes, st);
+    if (rc != B200PC_OK) return rc;
+    if (weight && B > 0 && N > 0) {
+        const long rows = (long)B * N;
+        three_weights_kernel<<<(int)((rows + 255) / 256), 256, 0, st>>>(dist, rows, variant, weight);
+        B200PC_LAUNCH_CHECK();
+    }
+    return B200PC_OK;
+}
+
+extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, const float *weight, int B, int S, int N,
+                                        int C, float *out, b200pc_stream_t stream) {
+    B200PC_REQUIRE(feat && idx && weight && out, "three_interpolate: null pointer");
+    if (B == 0 || N == 0) return B200PC_OK;
+    cudaStream_t st = as_stream(stream);
+    if (C % 4 == 0 && aligned16(feat) && aligned16(out)) {
+        const long total = (long)B * N * (C / 4);
+        interp_vec4_kernel<2><<<wave_grid(total, 256, 2), 256, 0, st>>>(reinterpret_cast<const float4 *>(feat), idx, weight, S,
+                                                                        C / 4, (long)N, total, reinterpret_cast<float4 *>(out));
+    } else {
+        const long total = (long)B * N * C;
+        interp_scalar_kernel<<<wave_grid(total, 256, 1), 256, 0, st>>>(feat, idx, weight, S, C, (long)N, total, out);
+    }
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}
+
+extern "C" int b200pc_three_interpolate_bwd(const float *gout, const float *feat, const int64_t *idx, const float *weight,
+                                            int B, int S, int N, int C, float *gfeat, float *gweight,
+                                            b200pc_stream_t stream) {
+    B200PC_REQUIRE(gout && feat && idx && weight && gfeat, "three_interpolate_bwd: null pointer");
+    if (B == 0 || N == 0) return B200PC_OK;
+    const long rows = (long)B * N;
+    interp_bwd_kernel<<<wave_grid(rows * 32, 256, 1), 256, 0, as_stream(stream)>>>(gout, feat, idx, weight, S, C, (long)N,
+                                                                                  rows, gfeat, gweight);
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}

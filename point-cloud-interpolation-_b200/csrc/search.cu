@@ -1,0 +1,529 @@
+// search.cu -- brute-force neighbour search on FP32 CUDA cores (sm_100a).
+//
+// One streaming skeleton serves four reference call sites (file:line relative to the reference):
+//   * kNN grouping           Utils/Layers.py:50-53          form 0, top-k
+//   * three-NN               Utils/Layers.py:180-182,       form 1, top-3
+//                            Utils/Pointnet2Utils.py:297-299
+//   * pytorch3d knn_points   Utils/Layers.py:220 ...        form 2, top-K   (also Chamfer, K=1)
+//   * query_ball_point       Utils/Pointnet2Utils.py:88-108 form 1, first-nsample-by-index
+//
+// Design (why it looks the way it does is argued in DESIGN.md):
+//   1. pack_refs_kernel turns refs [B,N,3] into 16-byte records grouped in PAIRS:
+//      {x0,x1,y0,y1} {z0,z1,w0,w1} (w = |r|^2 rounded as torch does, or 0 for the direct form),
+//      padded to a whole tile with records whose distance is +inf.
+//   2. search_kernel: one TMA-producer warp streams 8 KB tiles of those records into a 4-stage
+//      shared-memory ring with cp.async.bulk + mbarrier; consumer threads own Q queries each and
+//      evaluate 2 refs per instruction with FFMA2/FMUL2/FADD2 in EXACTLY the reference's rounding
+//      order.  The refs of a tile are read with broadcast LDS.128 (no bank conflicts).
+//   3. The per-pair cost is kept at "distance + half a min": a chunk of 8 refs is reduced with
+//      FMNMX3 and compared once against the query's current threshold tau; a hit only sets a bit
+//      in a register mask.  There is no branch and no list traffic in the hot loop.
+//   4. After at most 32 chunks the mask is drained: hit chunks are re-evaluated (bit-identical
+//      arithmetic) and true candidates are insertion-sorted into a per-query list that lives in
+//      shared memory, laid out [rank][query] so that lanes never conflict.  Refs are visited in
+//      increasing index order and insertion uses strict '<', which yields the total order
+//      (distance, index): ties go to the lower index, deterministically.
+//   5. When there are too few queries to fill 148 SMs the ref range is split over gridDim.z and
+//      a small merge kernel combines the partial lists.
+#include "search.cuh"
+
+#include <math_constants.h>
+
+namespace b200pc {
+
+constexpr int TILE = 512;                  // refs per shared-memory tile
+constexpr int TILE_BYTES = TILE * 16;      // 8 KB
+constexpr int STAGES = 4;                  // ring depth
+constexpr int CHUNK = 8;                   // refs per threshold test
+constexpr int CHUNKS_PER_TILE = TILE / CHUNK;
+constexpr int MAX_SPLIT = 32;
+constexpr int BAR_BYTES = 128;
+
+// ---------------------------------------------------------------------------------------------
+// 1. ref packing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float torch_sq_norm(float x, float y, float z) {
+    // torch.sum(p ** 2, -1): three roundings of the squares, then (xx + yy) + zz, never fused
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+__global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad, int form,
+                                 float4 *__restrict__ packed) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+    if (p >= n_pad / 2) return;
+    int b = blockIdx.y;
+    const float *r = ref + (size_t)b * N * 3;
+    float x[2], y[2], z[2], w[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int i = 2 * p + h;
+        if (i < N) {
+            x[h] = r[i * 3 + 0]; y[h] = r[i * 3 + 1]; z[h] = r[i * 3 + 2];
+            w[h] = form == B200PC_FORM_DIRECT ? 0.0f : torch_sq_norm(x[h], y[h], z[h]);
+        } else if (form == B200PC_FORM_DIRECT) {
+            x[h] = CUDART_INF_F; y[h] = 0.0f; z[h] = 0.0f; w[h] = 0.0f;   // (inf - q)^2 = inf
+        } else {
+            x[h] = 0.0f; y[h] = 0.0f; z[h] = 0.0f; w[h] = CUDART_INF_F;   // 0 + inf = inf
+        }
+    }
+    float4 *o = packed + ((size_t)b * (n_pad / 2) + p) * 2;
+    o[0] = make_float4(x[0], x[1], y[0], y[1]);
+    o[1] = make_float4(z[0], z[1], w[0], w[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. distance of one query against a PAIR of refs, in the reference's rounding order
+// ---------------------------------------------------------------------------------------------
+struct QueryConst {  // per-query splatted constants
+    f32x2 a0, a1, a2, a3;
+};
+
+template <int FORM>
+__device__ __forceinline__ QueryConst make_query(float x, float y, float z) {
+    QueryConst q;
+    if (FORM == B200PC_FORM_DIRECT) {
+        q.a0 = splat2(-x); q.a1 = splat2(-y); q.a2 = splat2(-z); q.a3 = 0ull;
+    } else {
+        // -2*(s.d) == s.(-2d) exactly: scaling by a power of two commutes with every rounding
+        q.a0 = splat2(-2.0f * x); q.a1 = splat2(-2.0f * y); q.a2 = splat2(-2.0f * z);
+        q.a3 = splat2(torch_sq_norm(x, y, z));
+    }
+    return q;
+}
+
+template <int FORM>
+__device__ __forceinline__ f32x2 pair_dist(const float4 &A, const float4 &Bv, const QueryConst &q) {
+    f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w), Z = pack2(Bv.x, Bv.y);
+    if (FORM == B200PC_FORM_DIRECT) {
+        // pytorch3d: d = fma(dz,dz, fma(dy,dy, dx*dx)); (r-q)^2 == (q-r)^2 bit for bit
+        f32x2 dx = add2(X, q.a0), dy = add2(Y, q.a1), dz = add2(Z, q.a2);
+        f32x2 t = mul2(dx, dx);
+        t = fma2(dy, dy, t);
+        return fma2(dz, dz, t);
+    }
+    // torch CPU (MKL sgemm, K=3): dot = fma(z,z', fma(y,y', x*x')); then two separate adds
+    f32x2 W = pack2(Bv.z, Bv.w);
+    f32x2 t = mul2(X, q.a0);
+    t = fma2(Y, q.a1, t);
+    t = fma2(Z, q.a2, t);
+    if (FORM == B200PC_FORM_REF_NORM_FIRST) {
+        t = add2(t, W);         // dist += |src|^2   (src = refs at the kNN call site)
+        return add2(t, q.a3);   // dist += |dst|^2
+    } else {
+        t = add2(t, q.a3);      // src = queries (ball query, three-NN)
+        return add2(t, W);
+    }
+}
+
+template <int FORM>
+__device__ __forceinline__ float chunk_min(const float4 (&A)[4], const float4 (&Bv)[4], const QueryConst &q) {
+    float d[8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) unpack2(pair_dist<FORM>(A[p], Bv[p], q), d[2 * p], d[2 * p + 1]);
+    float m0 = min3(d[0], d[1], d[2]);
+    float m1 = min3(d[3], d[4], d[5]);
+    float m2 = min3(d[6], d[7], m0);
+    return fminf(m1, m2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. the streaming search kernel
+// ---------------------------------------------------------------------------------------------
+struct SearchArgs {
+    const float4 *packed;  // [B][n_pad/2][2]
+    const float *qry;      // [B][S][3]
+    int N, n_pad, S, k;
+    float r2;              // ball radius^2 (fp32)
+    int n_split, tiles_per_split;
+    int64_t *idx_out;      // [B][S][k]   (n_split == 1)
+    float *dist_out;       // [B][S][k] or null
+    float *part_d;         // [B][S][n_split][k]  (top-k partial lists)
+    int *part_i;           // [B][S][n_split][k]
+    int *part_cnt;         // [B][S][n_split]     (ball partial counts)
+};
+
+template <int FORM, int MODE, int Q, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs P) {
+    constexpr int NCT = NCW * 32;   // consumer threads
+    constexpr int QPB = NCT * Q;    // queries per block
+    extern __shared__ __align__(128) unsigned char smem[];
+    const float4 *tiles = reinterpret_cast<const float4 *>(smem);
+    const uint32_t bar_base = smem_u32(smem + STAGES * TILE_BYTES);   // full[s] at +8s, empty[s] at +8(STAGES+s)
+    float *list_d = reinterpret_cast<float *>(smem + STAGES * TILE_BYTES + BAR_BYTES);
+    int *list_i = reinterpret_cast<int *>(list_d + (MODE == MODE_TOPK ? (size_t)P.k * QPB : 0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, split = blockIdx.z;
+    const int tile0 = split * P.tiles_per_split;
+    const int tile1 = min(tile0 + P.tiles_per_split, P.n_pad / TILE);
+    const int ntiles = tile1 - tile0;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_base + 8 * s, 1);
+            mbar_init(bar_base + 8 * (STAGES + s), NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ---------------- TMA producer: one lane streams the tiles of this split ----------------
+        if (lane == 0) {
+            const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * P.n_pad + (size_t)tile0 * TILE) * 16;
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % STAGES;
+                if (t >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((t / STAGES) & 1) ^ 1);
+                mbar_expect_tx(bar_base + 8 * s, TILE_BYTES);
+                bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)t * TILE_BYTES, TILE_BYTES, bar_base + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int ct = threadIdx.x;  // 0 .. NCT-1
+    QueryConst qc[Q];
+    float tau[Q];
+    int cnt[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const int qi = blockIdx.x * QPB + j * NCT + ct;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (qi < P.S) {
+            const float *qp = P.qry + ((size_t)b * P.S + qi) * 3;
+            x = qp[0]; y = qp[1]; z = qp[2];
+        }
+        qc[j] = make_query<FORM>(x, y, z);
+        cnt[j] = 0;
+        if (MODE == MODE_TOPK) {
+            tau[j] = CUDART_INF_F;
+            for (int s = 0; s < P.k; ++s) {
+                list_d[s * QPB + j * NCT + ct] = CUDART_INF_F;
+                list_i[s * QPB + j * NCT + ct] = 0;
+            }
+        } else {
+            tau[j] = P.r2;
+        }
+    }
+
+    int gpos = 0;  // chunks consumed in this split (drives the warm-up schedule)
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(bar_base + 8 * s, (t / STAGES) & 1);
+        const float4 *tp = tiles + (size_t)s * TILE;
+        const int tile_ref0 = (tile0 + t) * TILE;
+
+        int c = 0;
+        while (c < CHUNKS_PER_TILE) {
+            // warm-up: drain after 2,2,4,8,16 chunks so tau tightens quickly, then every 32
+            int nch = gpos < 32 ? max(2, gpos) : 32;
+            nch = min(nch, CHUNKS_PER_TILE - c);
+
+            uint32_t mask[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) mask[j] = 0u;
+            uint32_t bit = 1u;
+            const float4 *cp = tp + c * CHUNK;
+#pragma unroll 2
+            for (int cc = 0; cc < nch; ++cc, bit <<= 1, cp += CHUNK) {
+                float4 A[4], Bv[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) { A[p] = cp[2 * p]; Bv[p] = cp[2 * p + 1]; }
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    const float m = chunk_min<FORM>(A, Bv, qc[j]);
+                    const bool hit = MODE == MODE_TOPK ? (m < tau[j]) : (m <= tau[j]);
+                    if (hit) mask[j] |= bit;
+                }
+            }
+
+            // ---- drain: revisit hit chunks in index order, exact same arithmetic ----
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                uint32_t m = mask[j];
+                const int slot = j * NCT + ct;
+                while (m) {
+                    const int cc = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 *dp = tp + (c + cc) * CHUNK;
+                    const int ref0 = tile_ref0 + (c + cc) * CHUNK;
+#pragma unroll 1
+                    for (int p = 0; p < 4; ++p) {
+                        float dd[2];
+                        unpack2(pair_dist<FORM>(dp[2 * p], dp[2 * p + 1], qc[j]), dd[0], dd[1]);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float d = dd[h];
+                            const int ri = ref0 + 2 * p + h;
+                            if (MODE == MODE_TOPK) {
+                                if (d < tau[j]) {
+                                    int pos = P.k - 1;
+                                    while (pos > 0) {
+                                        const float pd = list_d[(pos - 1) * QPB + slot];
+                                        if (!(pd > d)) break;
+                                        list_d[pos * QPB + slot] = pd;
+                                        list_i[pos * QPB + slot] = list_i[(pos - 1) * QPB + slot];
+                                        --pos;
+                                    }
+                                    list_d[pos * QPB + slot] = d;
+                                    list_i[pos * QPB + slot] = ri;
+                                    tau[j] = list_d[(P.k - 1) * QPB + slot];
+                                }
+                            } else {
+                                if (d <= tau[j]) {
+                                    list_i[cnt[j] * QPB + slot] = ri;
+                                    if (++cnt[j] == P.k) { tau[j] = -CUDART_INF_F; m = 0u; }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            c += nch;
+            gpos += nch;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+    }
+
+    // ---------------- results ----------------
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const int qi = blockIdx.x * QPB + j * NCT + ct;
+        if (qi >= P.S) continue;
+        const int slot = j * NCT + ct;
+        const size_t row = (size_t)b * P.S + qi;
+        if (P.n_split == 1) {
+            int64_t *io = P.idx_out ? P.idx_out + row * P.k : nullptr;
+            if (MODE == MODE_TOPK) {
+                float *dout = P.dist_out ? P.dist_out + row * P.k : nullptr;
+                for (int s = 0; s < P.k; ++s) {
+                    if (io) io[s] = list_i[s * QPB + slot];
+                    if (dout) dout[s] = list_d[s * QPB + slot];
+                }
+            } else {
+                const int first = cnt[j] > 0 ? list_i[slot] : P.N;
+                for (int s = 0; s < P.k; ++s) io[s] = s < cnt[j] ? list_i[s * QPB + slot] : first;
+            }
+        } else {
+            const size_t prow = (row * P.n_split + split) * P.k;
+            if (MODE == MODE_TOPK) {
+                for (int s = 0; s < P.k; ++s) {
+                    P.part_d[prow + s] = list_d[s * QPB + slot];
+                    P.part_i[prow + s] = list_i[s * QPB + slot];
+                }
+            } else {
+                P.part_cnt[row * P.n_split + split] = cnt[j];
+                for (int s = 0; s < cnt[j]; ++s) P.part_i[prow + s] = list_i[s * QPB + slot];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. merge of partial lists (only when the ref range was split)
+// ---------------------------------------------------------------------------------------------
+__global__ void merge_topk_kernel(const float *__restrict__ part_d, const int *__restrict__ part_i, int rows,
+                                  int n_split, int k, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    unsigned char head[MAX_SPLIT];
+#pragma unroll
+    for (int s = 0; s < MAX_SPLIT; ++s) head[s] = 0;
+    const float *pd = part_d + (size_t)row * n_split * k;
+    const int *pi = part_i + (size_t)row * n_split * k;
+    for (int o = 0; o < k; ++o) {
+        float best = CUDART_INF_F;
+        int bs = 0;
+        // splits hold disjoint, increasing index ranges: strict '<' keeps the lower index on ties
+        for (int s = 0; s < n_split; ++s) {
+            const int h = head[s];
+            const float d = h < k ? pd[s * k + h] : CUDART_INF_F;
+            if (d < best) { best = d; bs = s; }
+        }
+        const int h = head[bs];
+        if (idx_out) idx_out[(size_t)row * k + o] = pi[bs * k + h];
+        if (dist_out) dist_out[(size_t)row * k + o] = best;
+        head[bs] = h + 1;
+    }
+}
+
+__global__ void merge_ball_kernel(const int *__restrict__ part_i, const int *__restrict__ part_cnt, int rows,
+                                  int n_split, int k, int N, int64_t *__restrict__ idx_out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    int64_t *o = idx_out + (size_t)row * k;
+    int n = 0;
+    for (int s = 0; s < n_split && n < k; ++s) {
+        const int c = part_cnt[(size_t)row * n_split + s];
+        const int *pi = part_i + ((size_t)row * n_split + s) * k;
+        for (int e = 0; e < c && n < k; ++e) o[n++] = pi[e];
+    }
+    const int64_t first = n > 0 ? o[0] : (int64_t)N;
+    for (; n < k; ++n) o[n] = first;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. planning + launch
+// ---------------------------------------------------------------------------------------------
+static size_t list_bytes(int k, int qpb, int mode) { return (size_t)k * qpb * (mode == MODE_TOPK ? 8 : 4); }
+static const size_t kMaxSmem = 227 * 1024;
+
+bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
+    const int sms = sm_count();
+    // candidate CTA shapes, largest first: {Q, consumer warps}
+    static const int shapes[][2] = {{2, 8}, {2, 4}, {1, 4}, {1, 2}};
+    const size_t fixed = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
+    int pick = -1;
+    for (int i = 0; i < 4; ++i) {
+        const int qpb = shapes[i][0] * shapes[i][1] * 32;
+        // keep at least two CTAs per SM resident while the lists fit
+        if (fixed + list_bytes(k, qpb, mode) <= kMaxSmem / 2 || i == 3) {
+            if (fixed + list_bytes(k, qpb, mode) > kMaxSmem) return false;
+            pick = i;
+            break;
+        }
+    }
+    // too few CTAs to occupy the machine: shrink the CTA first (more CTAs), then split the refs
+    while (pick < 3) {
+        const int qpb = shapes[pick][0] * shapes[pick][1] * 32;
+        const long ctas = (long)((S + qpb - 1) / qpb) * B;
+        if (ctas >= 2L * sms) break;
+        ++pick;
+    }
+    pl->q_per_thread = shapes[pick][0];
+    pl->consumer_warps = shapes[pick][1];
+    pl->q_per_block = shapes[pick][0] * shapes[pick][1] * 32;
+    pl->n_pad = (int)align_up((size_t)N, TILE);
+    pl->n_tiles = pl->n_pad / TILE;
+    const long ctas = (long)((S + pl->q_per_block - 1) / pl->q_per_block) * B;
+    int want = (int)((2L * sms + ctas - 1) / ctas);
+    if (want < 1) want = 1;
+    if (want > MAX_SPLIT) want = MAX_SPLIT;
+    if (want > pl->n_tiles) want = pl->n_tiles;
+    pl->tiles_per_split = (pl->n_tiles + want - 1) / want;
+    pl->n_split = (pl->n_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
+    pl->smem_bytes = fixed + list_bytes(k, pl->q_per_block, mode);
+    pl->packed_bytes = align_up((size_t)B * pl->n_pad * 16, 256);
+    pl->part_bytes = 0;
+    if (pl->n_split > 1) {
+        const size_t rows = (size_t)B * S * pl->n_split;
+        pl->part_bytes = align_up(rows * k * 4, 256) * (mode == MODE_TOPK ? 2 : 1) + align_up(rows * 4, 256);
+    }
+    pl->total_bytes = pl->packed_bytes + pl->part_bytes;
+    return true;
+}
+
+template <int FORM, int MODE, int Q, int NCW>
+static int launch_one(const SearchArgs &a, const SearchPlan &pl, int B, cudaStream_t st) {
+    auto kern = search_kernel<FORM, MODE, Q, NCW>;
+    B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    dim3 grid((a.S + pl.q_per_block - 1) / pl.q_per_block, B, pl.n_split);
+    kern<<<grid, (NCW + 1) * 32, pl.smem_bytes, st>>>(a);
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}
+
+template <int FORM, int MODE>
+static int launch_shape(const SearchArgs &a, const SearchPlan &pl, int B, cudaStream_t st) {
+    if (pl.q_per_thread == 2 && pl.consumer_warps == 8) return launch_one<FORM, MODE, 2, 8>(a, pl, B, st);
+    if (pl.q_per_thread == 2 && pl.consumer_warps == 4) return launch_one<FORM, MODE, 2, 4>(a, pl, B, st);
+    if (pl.q_per_thread == 1 && pl.consumer_warps == 4) return launch_one<FORM, MODE, 1, 4>(a, pl, B, st);
+    return launch_one<FORM, MODE, 1, 2>(a, pl, B, st);
+}
+
+static int run_search(const float *ref, const float *qry, int B, int N, int S, int k, int form, int mode, float r2,
+                      int64_t *idx, float *dist, void *ws, size_t ws_bytes, cudaStream_t st) {
+    B200PC_REQUIRE(ref && qry, "search: null input pointer");
+    B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && k >= 1, "search: bad sizes B=%d N=%d S=%d k=%d", B, N, S, k);
+    B200PC_REQUIRE(idx || dist, "search: no output requested");
+    if (B == 0 || S == 0) return B200PC_OK;
+    SearchPlan pl;
+    if (!plan_search(B, N, S, k, mode, &pl)) {
+        set_error("search: list length k=%d does not fit in shared memory", k);
+        return B200PC_EINVAL;
+    }
+    if (!ws || ws_bytes < pl.total_bytes) {
+        set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, pl.total_bytes);
+        return B200PC_EWORKSPACE;
+    }
+    B200PC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "search: workspace must be 16-byte aligned");
+
+    char *w = static_cast<char *>(ws);
+    float4 *packed = reinterpret_cast<float4 *>(w);
+    {
+        dim3 grid((pl.n_pad / 2 + 255) / 256, B);
+        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, form, packed);
+        B200PC_LAUNCH_CHECK();
+    }
+    SearchArgs a;
+    a.packed = packed; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
+    a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
+    a.idx_out = idx; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
+    if (pl.n_split > 1) {
+        const size_t rows = (size_t)B * S * pl.n_split;
+        char *p = w + pl.packed_bytes;
+        a.part_i = reinterpret_cast<int *>(p); p += align_up(rows * k * 4, 256);
+        if (mode == MODE_TOPK) { a.part_d = reinterpret_cast<float *>(p); p += align_up(rows * k * 4, 256); }
+        a.part_cnt = reinterpret_cast<int *>(p);
+    }
+    int rc;
+    if (mode == MODE_BALL) rc = launch_shape<B200PC_FORM_QRY_NORM_FIRST, MODE_BALL>(a, pl, B, st);
+    else if (form == B200PC_FORM_REF_NORM_FIRST) rc = launch_shape<B200PC_FORM_REF_NORM_FIRST, MODE_TOPK>(a, pl, B, st);
+    else if (form == B200PC_FORM_QRY_NORM_FIRST) rc = launch_shape<B200PC_FORM_QRY_NORM_FIRST, MODE_TOPK>(a, pl, B, st);
+    else rc = launch_shape<B200PC_FORM_DIRECT, MODE_TOPK>(a, pl, B, st);
+    if (rc != B200PC_OK) return rc;
+
+    if (pl.n_split > 1) {
+        const int rows = B * S;
+        if (mode == MODE_TOPK)
+            merge_topk_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a.part_d, a.part_i, rows, pl.n_split, k, idx, dist);
+        else
+            merge_ball_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a.part_i, a.part_cnt, rows, pl.n_split, k, N, idx);
+        B200PC_LAUNCH_CHECK();
+    }
+    return B200PC_OK;
+}
+
+int run_topk(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx, float *dist,
+             void *ws, size_t ws_bytes, cudaStream_t st) {
+    B200PC_REQUIRE(form >= 0 && form <= 2, "knn: unknown distance form %d", form);
+    B200PC_REQUIRE(k <= N, "knn: k=%d exceeds the number of reference points N=%d", k, N);
+    return run_search(ref, qry, B, N, S, k, form, MODE_TOPK, 0.f, idx, dist, ws, ws_bytes, st);
+}
+
+int run_ball(const float *ref, const float *qry, int B, int N, int S, float r2, int nsample, int64_t *idx,
+             void *ws, size_t ws_bytes, cudaStream_t st) {
+    B200PC_REQUIRE(idx, "ball_query: null output pointer");
+    return run_search(ref, qry, B, N, S, nsample, B200PC_FORM_QRY_NORM_FIRST, MODE_BALL, r2, idx, nullptr, ws,
+                      ws_bytes, st);
+}
+
+}  // namespace b200pc
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace b200pc;
+
+extern "C" size_t b200pc_search_workspace_bytes(int B, int N, int S, int k) {
+    if (B <= 0 || N <= 0 || S <= 0 || k <= 0) return 256;
+    SearchPlan a, c;
+    size_t need = 256;
+    if (plan_search(B, N, S, k, MODE_TOPK, &a)) need = a.total_bytes > need ? a.total_bytes : need;
+    if (plan_search(B, N, S, k, MODE_BALL, &c)) need = c.total_bytes > need ? c.total_bytes : need;
+    return need;
+}
+
+extern "C" int b200pc_knn(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
+                          float *dist, void *workspace, size_t workspace_bytes, b200pc_stream_t stream) {
+    return run_topk(ref, qry, B, N, S, k, form, idx, dist, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int b200pc_ball_query(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
+                                 int64_t *idx, void *workspace, size_t workspace_bytes, b200pc_stream_t stream) {
+    B200PC_REQUIRE(nsample >= 1, "ball_query: nsample must be >= 1");
+    return run_ball(xyz, new_xyz, B, N, S, r2, nsample, idx, workspace, workspace_bytes, as_stream(stream));
+}

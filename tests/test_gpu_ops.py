@@ -1,0 +1,167 @@
+"""GPU parity of FPS, index_points, three_interpolate, square_distance and Chamfer vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from b200pc import ops, pointnet2_utils as P, pytorch3d_shim as S3, synth
+from oracle import strict
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+# ---------------------------------------------------------------- square_distance (a1)
+@pytest.mark.parametrize("B,N,M", [(2, 1024, 256), (1, 300, 1001), (3, 17, 5), (1, 4096, 4096)])
+def test_square_distance_bit_exact(cuda_dev, B, N, M):
+    a, b = synth.batch_pairs(60, B, max(N, M))
+    src, dst = a[:, :N].copy(), b[:, :M].copy()
+    out = P.square_distance(_t(src, cuda_dev), _t(dst, cuda_dev))
+    np.testing.assert_array_equal(_bits(out.cpu().numpy()), _bits(strict.square_distance(src, dst)))
+
+
+def test_square_distance_non_contiguous_input(cuda_dev):
+    a, b = synth.batch_pairs(61, 2, 512)
+    src = _t(a, cuda_dev).permute(0, 2, 1).contiguous().permute(0, 2, 1)   # SA-MSG passes a permuted view
+    out = P.square_distance(src, _t(b, cuda_dev))
+    np.testing.assert_array_equal(_bits(out.cpu().numpy()), _bits(strict.square_distance(a, b)))
+
+
+# ---------------------------------------------------------------- farthest_point_sample (a3)
+FPS_CASES = [(1, 16384, 1024), (2, 1024, 256), (2, 256, 64), (3, 64, 16), (1, 8192, 2048),
+             (2, 5000, 500), (1, 40000, 256), (1, 70000, 128), (16, 16384, 64), (1, 3, 3)]
+
+
+@pytest.mark.parametrize("B,N,npoint", FPS_CASES)
+def test_fps_bit_exact(cuda_dev, B, N, npoint):
+    a, _ = synth.batch_pairs(70, B, N)
+    start = np.random.default_rng(N).integers(0, N, size=B)
+    out = P.farthest_point_sample_from(_t(a, cuda_dev), npoint, _t(start, cuda_dev))
+    assert out.dtype == torch.int64 and out.shape == (B, npoint)
+    np.testing.assert_array_equal(out.cpu().numpy(), strict.farthest_point_sample(a, npoint, start))
+
+
+def test_fps_duplicates_first_argmax(cuda_dev):
+    # padded-duplicate cloud (the reference's loaders pad short frames by re-drawing points)
+    a, _ = synth.batch_pairs(71, 1, 2048)
+    dup = np.concatenate([a, a[:, :1024]], 1)
+    start = np.array([7])
+    out = P.farthest_point_sample_from(_t(dup, cuda_dev), 2500, _t(start, cuda_dev))
+    np.testing.assert_array_equal(out.cpu().numpy(), strict.farthest_point_sample(dup, 2500, start))
+
+
+def test_fps_consumes_cpu_rng_like_reference(cuda_dev):
+    a, _ = synth.batch_pairs(72, 2, 1024)
+    torch.manual_seed(123)
+    expect_start = torch.randint(0, 1024, (2,), dtype=torch.long)
+    torch.manual_seed(123)
+    out = P.farthest_point_sample(_t(a, cuda_dev), 8)
+    assert torch.equal(out[:, 0].cpu(), expect_start)
+
+
+# ---------------------------------------------------------------- index_points (a6)
+@pytest.mark.parametrize("C", [3, 1, 64, 128, 130, 256])
+def test_index_points_2d_and_3d_idx(cuda_dev, C):
+    rng = np.random.default_rng(C)
+    pts = rng.normal(size=(2, 1000, C)).astype(np.float32)
+    i2 = rng.integers(0, 1000, size=(2, 333))
+    i3 = rng.integers(0, 1000, size=(2, 77, 16))
+    for idx in (i2, i3):
+        out = P.index_points(_t(pts, cuda_dev), _t(idx, cuda_dev))
+        assert out.shape == idx.shape + (C,)
+        np.testing.assert_array_equal(out.cpu().numpy(), strict.index_points(pts, idx))
+
+
+def test_index_points_int32_and_negative_indices(cuda_dev):
+    pts = np.arange(2 * 10 * 4, dtype=np.float32).reshape(2, 10, 4)
+    idx = np.array([[0, -1, 9, -10], [3, 3, -2, 5]], np.int32)
+    out = P.index_points(_t(pts, cuda_dev), torch.from_numpy(idx).to(cuda_dev))
+    np.testing.assert_array_equal(out.cpu().numpy(), strict.index_points(pts, idx.astype(np.int64)))
+
+
+def test_index_points_out_of_range_raises_indexerror(cuda_dev, monkeypatch):
+    monkeypatch.setattr(ops, "CHECK_BOUNDS", True)
+    pts = torch.zeros(1, 10, 4, device=cuda_dev)
+    with pytest.raises(IndexError):
+        P.index_points(pts, torch.tensor([[10]], device=cuda_dev))
+
+
+def test_index_points_backward_scatter_add(cuda_dev):
+    rng = np.random.default_rng(1)
+    pts = torch.tensor(rng.normal(size=(2, 50, 8)).astype(np.float32), device=cuda_dev, requires_grad=True)
+    idx = torch.tensor(rng.integers(0, 50, size=(2, 40, 4)), device=cuda_dev)
+    g = torch.tensor(rng.normal(size=(2, 40, 4, 8)).astype(np.float32), device=cuda_dev)
+    P.index_points(pts, idx).backward(g)
+    ref = pts.detach().clone().requires_grad_(True)
+    ref[torch.arange(2, device=cuda_dev).view(2, 1, 1), idx].backward(g)
+    torch.testing.assert_close(pts.grad, ref.grad, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- three_interpolate (a5)
+@pytest.mark.parametrize("C", [128, 256, 3, 30])
+def test_three_interpolate_forward(cuda_dev, C):
+    a, _ = synth.batch_pairs(80, 2, 4096)
+    known = a[:, ::8].copy()
+    feats = np.random.default_rng(C).normal(size=(2, known.shape[1], C)).astype(np.float32)
+    od, oi = strict.three_nn(a, known)
+    for variant in (0, 1):
+        ow = strict.three_weights(od, variant)
+        out = P.three_interpolate(_t(feats, cuda_dev), _t(oi, cuda_dev), _t(ow, cuda_dev))
+        exp = strict.three_interpolate(feats, oi, ow)
+        np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=1e-5, atol=1e-6)   # north_star tolerance
+
+
+def test_three_interpolate_backward(cuda_dev):
+    rng = np.random.default_rng(2)
+    feat = torch.tensor(rng.normal(size=(2, 30, 16)).astype(np.float32), device=cuda_dev, requires_grad=True)
+    w = torch.tensor(rng.uniform(0.1, 1, size=(2, 100, 3)).astype(np.float32), device=cuda_dev, requires_grad=True)
+    idx = torch.tensor(rng.integers(0, 30, size=(2, 100, 3)), device=cuda_dev)
+    g = torch.tensor(rng.normal(size=(2, 100, 16)).astype(np.float32), device=cuda_dev)
+    P.three_interpolate(feat, idx, w).backward(g)
+    f2 = feat.detach().clone().requires_grad_(True); w2 = w.detach().clone().requires_grad_(True)
+    gathered = f2[torch.arange(2, device=cuda_dev).view(2, 1, 1), idx]
+    (gathered * w2.unsqueeze(-1)).sum(2).backward(g)
+    torch.testing.assert_close(feat.grad, f2.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(w.grad, w2.grad, rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- chamfer (a9)
+@pytest.mark.parametrize("B,N,M", [(2, 2048, 2048), (1, 1000, 1500), (4, 8192, 8192)])
+def test_chamfer_forward(cuda_dev, B, N, M):
+    a, b = synth.batch_pairs(90, B, max(N, M))
+    x, y = a[:, :N].copy(), b[:, :M].copy()
+    loss, dx, ix, dy, iy = ops.chamfer(_t(x, cuda_dev), _t(y, cuda_dev))
+    ol, odx, oix, ody, oiy = strict.chamfer(x, y)
+    np.testing.assert_array_equal(ix.cpu().numpy(), oix)
+    np.testing.assert_array_equal(iy.cpu().numpy(), oiy)
+    np.testing.assert_array_equal(_bits(dx.cpu().numpy()), _bits(odx))
+    np.testing.assert_array_equal(_bits(dy.cpu().numpy()), _bits(ody))
+    assert abs(loss.item() - ol) <= 1e-5 * abs(ol)      # north_star: 1e-5 relative
+    l2, none = S3.chamfer_distance(_t(x, cuda_dev), _t(y, cuda_dev))
+    assert none is None and l2.dim() == 0 and l2.item() == loss.item()
+
+
+def test_chamfer_backward_matches_autograd_of_dense_formula(cuda_dev):
+    a, b = synth.batch_pairs(91, 2, 512)
+    x = _t(a, cuda_dev).requires_grad_(True); y = _t(b, cuda_dev).requires_grad_(True)
+    S3.chamfer_distance(x, y)[0].backward()
+    x2 = x.detach().clone().requires_grad_(True); y2 = y.detach().clone().requires_grad_(True)
+    d = ((x2.unsqueeze(2) - y2.unsqueeze(1)) ** 2).sum(-1)
+    (d.min(2)[0].mean(1) + d.min(1)[0].mean(1)).mean().backward()
+    torch.testing.assert_close(x.grad, x2.grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(y.grad, y2.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_chamfer_loss_reference_layout(cuda_dev):
+    # Utils/Utils.py:39-48 passes [B,3,N] tensors permuted to [B,N,3] (non-contiguous views)
+    a, b = synth.batch_pairs(92, 2, 1024)
+    pc1 = _t(a, cuda_dev).permute(0, 2, 1).contiguous(); pc2 = _t(b, cuda_dev).permute(0, 2, 1).contiguous()
+    loss, _ = S3.chamfer_distance(pc1.permute(0, 2, 1), pc2.permute(0, 2, 1))
+    ol = strict.chamfer(a, b)[0]
+    assert abs(loss.item() - ol) <= 1e-5 * abs(ol)

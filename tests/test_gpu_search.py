@@ -1,0 +1,173 @@
+"""GPU parity of the neighbour searches (kNN, three-NN, knn_points, ball query) against the strict
+oracle.  Bar: indices and distances BIT-EXACT on every row, ties included (the oracle and the
+kernels both realise the total order (distance, index); SURVEY Appendix A.4 rule 3)."""
+import numpy as np
+import pytest
+import torch
+
+from b200pc import ops, pointnet2_utils as P, pytorch3d_shim as S3, synth
+from oracle import strict
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+CASES = [
+    # (B, N refs, S queries, k)   -- shapes from SURVEY section 8a plus ragged/edge sizes
+    (2, 4096, 2048, 16),
+    (1, 256, 256, 64),      # FlowEmbedding, Models.py:33
+    (2, 16, 64, 8),         # SetUpConv 64x16
+    (1, 64, 256, 8),
+    (1, 1000, 777, 1),      # ragged: N, S not multiples of anything
+    (3, 513, 31, 3),        # one ref past a tile boundary
+    (1, 5, 9, 5),           # k == N
+    (1, 2048, 100, 32),
+]
+
+
+@pytest.mark.parametrize("B,N,S,k", CASES)
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_knn_matches_strict_oracle(cuda_dev, B, N, S, k, form):
+    a, b = synth.batch_pairs(10, B, max(N, S))
+    ref, qry = a[:, :N].copy(), b[:, :S].copy()
+    idx, dist = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), k, form, want_dist=True)
+    oi, od = strict.knn(ref, qry, k, form)
+    assert idx.dtype == torch.int64 and idx.shape == (B, S, k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(_bits(dist.cpu().numpy()), _bits(od))
+
+
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_knn_tie_stress_lowest_index_wins(cuda_dev, form):
+    # grid-snapped coordinates: all arithmetic exact, many exactly equal distances and duplicates
+    ref = synth.grid_snapped(7, 2, 3000, span=6)
+    qry = synth.grid_snapped(8, 2, 500, span=6)
+    idx, dist = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), 16, form, want_dist=True)
+    oi, od = strict.knn(ref, qry, 16, form)
+    ties = (od[:, :, 1:] == od[:, :, :-1]).any(-1).mean()
+    assert ties > 0.5, "the stress set is supposed to be full of ties"
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(_bits(dist.cpu().numpy()), _bits(od))
+
+
+def test_knn_split_path_small_query_count(cuda_dev):
+    # few queries against many refs -> the ref range is split over gridDim.z and merged
+    a, b = synth.batch_pairs(3, 1, 16384)
+    ref, qry = a, b[:, :1024].copy()
+    for k, form in ((8, 0), (16, 2), (3, 1)):
+        idx, dist = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), k, form, want_dist=True)
+        oi, od = strict.knn(ref, qry, k, form)
+        np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+        np.testing.assert_array_equal(_bits(dist.cpu().numpy()), _bits(od))
+
+
+def test_knn_sorted_input_order_worst_case(cuda_dev):
+    # refs sorted by decreasing distance from the queries' region: every ref is a candidate
+    rng = np.random.default_rng(0)
+    ref = np.sort(rng.uniform(1.0, 50.0, size=(1, 3000, 1)).astype(np.float32), axis=1)[:, ::-1]
+    ref = np.concatenate([ref, np.zeros_like(ref), np.zeros_like(ref)], -1).copy()
+    qry = rng.normal(0, 0.1, size=(1, 200, 3)).astype(np.float32)
+    idx = P.knn_point(16, _t(ref, cuda_dev), _t(qry, cuda_dev))
+    np.testing.assert_array_equal(idx.cpu().numpy(), strict.knn_point(16, ref, qry))
+
+
+def test_knn_k_larger_than_n_raises(cuda_dev):
+    ref = torch.zeros(1, 4, 3, device=cuda_dev); qry = torch.zeros(1, 2, 3, device=cuda_dev)
+    with pytest.raises(RuntimeError):
+        P.knn_point(5, ref, qry)
+
+
+def test_cpu_tensor_is_rejected_no_fallback():
+    with pytest.raises(RuntimeError):
+        P.knn_point(2, torch.zeros(1, 4, 3), torch.zeros(1, 2, 3))
+
+
+BALL_CASES = [
+    # (B, N, S, radius, nsample)  -- FlowNet3D SetConv shapes (Models.py:31-35) and C2's
+    (1, 16384, 1024, 0.5, 16),
+    (2, 1024, 256, 1.0, 16),
+    (1, 256, 64, 2.0, 8),
+    (2, 64, 16, 4.0, 8),
+    (2, 4096, 4096, 1.0, 32),
+    (1, 999, 333, 0.3, 16),
+    (1, 3000, 500, 0.1, 32),   # ISAPCI SA-MSG radius: mostly tiny / empty balls
+]
+
+
+@pytest.mark.parametrize("B,N,S,radius,nsample", BALL_CASES)
+def test_ball_query_matches_strict_oracle(cuda_dev, B, N, S, radius, nsample):
+    a, b = synth.batch_pairs(20, B, max(N, S))
+    xyz, new_xyz = a[:, :N].copy(), b[:, :S].copy()
+    out = P.query_ball_point(radius, nsample, _t(xyz, cuda_dev), _t(new_xyz, cuda_dev))
+    exp = strict.query_ball_point(radius, nsample, xyz, new_xyz)
+    assert out.dtype == torch.int64 and out.shape == (B, S, nsample)
+    np.testing.assert_array_equal(out.cpu().numpy(), exp)
+
+
+def test_ball_query_empty_ball_sentinel_is_n(cuda_dev):
+    xyz = np.zeros((1, 100, 3), np.float32); xyz[0, :, 0] = np.arange(100)
+    q = np.array([[[1000.0, 0, 0], [5.2, 0, 0]]], np.float32)
+    out = P.query_ball_point(0.5, 4, _t(xyz, cuda_dev), _t(q, cuda_dev)).cpu().numpy()
+    assert (out[0, 0] == 100).all()          # the reference's out-of-range sentinel, not clamped
+    np.testing.assert_array_equal(out[0, 1], [5, 5, 5, 5])
+
+
+def test_ball_query_subset_queries_self_included(cuda_dev):
+    # queries are a subset of the refs (the SetConv situation): d(self) is ~0 but may be slightly negative
+    a, _ = synth.batch_pairs(30, 2, 4096)
+    q = a[:, ::4].copy()
+    out = P.query_ball_point(0.5, 16, _t(a, cuda_dev), _t(q, cuda_dev))
+    np.testing.assert_array_equal(out.cpu().numpy(), strict.query_ball_point(0.5, 16, a, q))
+
+
+def test_three_nn_and_weights(cuda_dev):
+    a, _ = synth.batch_pairs(40, 2, 4096)
+    known = a[:, ::16].copy()   # 256 sparse points
+    for variant in (0, 1):
+        dist, idx, w = P.three_nn_weights(_t(a, cuda_dev), _t(known, cuda_dev), variant=variant)
+        od, oi = strict.three_nn(a, known)
+        np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+        np.testing.assert_array_equal(_bits(dist.cpu().numpy()), _bits(od))
+        ow = strict.three_weights(od, variant)
+        # tolerance stated by north_star: 1e-5 relative on fp32 values
+        np.testing.assert_allclose(w.cpu().numpy(), ow, rtol=1e-5, atol=1e-12)
+
+
+def test_knn_points_shim_contract(cuda_dev):
+    a, b = synth.batch_pairs(50, 2, 2048)
+    p1, p2 = _t(b, cuda_dev), _t(a, cuda_dev)
+    r = S3.knn_points(p1, p2, K=16, return_nn=True)
+    od, oi = strict.knn_points(b, a, 16)
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(_bits(r.dists.cpu().numpy()), _bits(od))
+    np.testing.assert_array_equal(r.knn.cpu().numpy(), strict.index_points(a, oi))
+    g = S3.knn_gather(p2, r.idx)
+    assert torch.equal(g, r.knn)
+    # K=1 (PolyPCI.rebuild, Models_V1.py:113)
+    r1 = S3.knn_points(p1, p2, K=1, return_nn=True)
+    assert torch.equal(r1.idx, r.idx[:, :, :1])
+
+
+def test_c2_full_size_properties(cuda_dev):
+    """BASELINE config 2 at full size (B=8, 16384 x 16384, k=16): sortedness, self-consistency
+    of distances, and a sampled exact check against the oracle."""
+    a, b = synth.batch_pairs(0, 8, 16384)
+    ref, qry = _t(a, cuda_dev), _t(b, cuda_dev)
+    idx, dist = ops.knn_search(ref, qry, 16, 0, want_dist=True)
+    d = dist.cpu().numpy(); i = idx.cpu().numpy()
+    assert (np.diff(d, axis=-1) >= 0).all()
+    assert i.min() >= 0 and i.max() < 16384
+    assert all(len(set(r)) == 16 for r in i[0, :64])
+    sel = np.arange(0, 16384, 97)
+    oi, od = strict.knn(a[:2], b[:2, sel], 16, 0)
+    np.testing.assert_array_equal(i[:2, sel], oi)
+    np.testing.assert_array_equal(_bits(d[:2, sel]), _bits(od))
+    ball = P.query_ball_point(1.0, 32, ref, qry).cpu().numpy()
+    np.testing.assert_array_equal(ball[:1, sel], strict.query_ball_point(1.0, 32, a[:1], b[:1, sel]))
