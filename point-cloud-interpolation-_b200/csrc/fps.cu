@@ -27,7 +27,7 @@ constexpr int FPS_T = 512;        // threads per CTA
 constexpr int FPS_WARPS = FPS_T / 32;
 constexpr int FPS_MAX_CLUSTER = 16;
 
-struct FpsRecord {  // what a CTA tells its peers each round
+struct __align__(16) FpsRecord {  // what a CTA tells its peers each round
     unsigned int bits;  // float bits of the CTA-wide max of min-dist
     int idx;            // lowest point index attaining it
     float x, y, z;      // its coordinates

@@ -28,6 +28,7 @@
 #include "search.cuh"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace b200pc {
 
@@ -208,7 +209,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs
         }
     }
 
-    int gpos = 0;  // chunks consumed in this split (drives the warm-up schedule)
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % STAGES;
         mbar_wait(bar_base + 8 * s, (t / STAGES) & 1);
@@ -217,9 +217,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs
 
         int c = 0;
         while (c < CHUNKS_PER_TILE) {
-            // warm-up: drain after 2,2,4,8,16 chunks so tau tightens quickly, then every 32
-            int nch = gpos < 32 ? max(2, gpos) : 32;
-            nch = min(nch, CHUNKS_PER_TILE - c);
+            // warm-up (first tile of the split only): drain after 2,2,4,8,16 chunks so that tau
+            // tightens quickly; afterwards every 32 chunks (the width of the hit mask).
+            int nch = 32;
+            if (t == 0 && c < 32) nch = c < 2 ? 2 : c;
+            if (nch > CHUNKS_PER_TILE - c) nch = CHUNKS_PER_TILE - c;
 
             uint32_t mask[Q];
 #pragma unroll
@@ -282,7 +284,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs
                 }
             }
             c += nch;
-            gpos += nch;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
@@ -329,7 +330,7 @@ __global__ void merge_topk_kernel(const float *__restrict__ part_d, const int *_
                                   int n_split, int k, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
-    unsigned char head[MAX_SPLIT];
+    unsigned short head[MAX_SPLIT];
 #pragma unroll
     for (int s = 0; s < MAX_SPLIT; ++s) head[s] = 0;
     const float *pd = part_d + (size_t)row * n_split * k;
@@ -393,6 +394,11 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
         if (ctas >= 2L * sms) break;
         ++pick;
     }
+    // tuning / debugging overrides (not part of the ABI): B200PC_FORCE_SHAPE=0..3, B200PC_FORCE_SPLIT=n
+    if (const char *e = getenv("B200PC_FORCE_SHAPE")) {
+        const int f = atoi(e);
+        if (f >= 0 && f < 4 && fixed + list_bytes(k, shapes[f][0] * shapes[f][1] * 32, mode) <= kMaxSmem) pick = f;
+    }
     pl->q_per_thread = shapes[pick][0];
     pl->consumer_warps = shapes[pick][1];
     pl->q_per_block = shapes[pick][0] * shapes[pick][1] * 32;
@@ -401,6 +407,8 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     const long ctas = (long)((S + pl->q_per_block - 1) / pl->q_per_block) * B;
     int want = (int)((2L * sms + ctas - 1) / ctas);
     if (want < 1) want = 1;
+    if (want > MAX_SPLIT) want = MAX_SPLIT;
+    if (const char *e = getenv("B200PC_FORCE_SPLIT")) { const int f = atoi(e); if (f >= 1) want = f; }
     if (want > MAX_SPLIT) want = MAX_SPLIT;
     if (want > pl->n_tiles) want = pl->n_tiles;
     pl->tiles_per_split = (pl->n_tiles + want - 1) / want;
