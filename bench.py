@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the geometric hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--extras 0|1]
+
+Workload (BASELINE.json configs[1], "C2"): knn_point k=16, 16384 queries vs 16384 refs, batch 8,
+on synthetic HDL-64-shaped frame pairs (b200pc.synth, seeds fixed by pair index).  One "step" is one
+pass of knn_point over that batch.  Metric: kNN Gqueries/s, whole job over all ranks (weak scaling:
+every rank owns its own 8 frame pairs, no data-path collective).
+
+Printed JSON line (rank 0): value = device-resident throughput; e2e = the same call with HOST
+(pinned) buffers, H2D + D2H inside the timed region; roofline = FP32 CUDA-core roofline of the
+search kernel (8 FLOP per (query, ref) pair); cpu_baseline = the reference's torch
+CPU algorithm (oracle/ref_torch.py) timed on this box's host cores on a bounded sample.
+`--impl reference` times only that CPU path, on the same config, and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "point-cloud-interpolation-_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+NPTS = 16384
+BATCH = 8
+K_NN = 16
+FLOP_PER_PAIR = 8.0                       # the reference's own un-fused count
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 x max SM clock
+METRIC = "knn_point_gqueries_per_s"
+UNIT = "Gqueries/s"
+WORKLOAD = "C2: knn_point k=16, 16384 queries x 16384 refs, batch 8 per GPU, synthetic HDL-64 pairs"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--extras", type=int, default=1, help="also time the other kernels of the path (rank 0)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_knn(a, b, reps, queries=NPTS):
+    """the reference's CPU algorithm for the step (square_distance + topk(dim=1), Utils/Layers.py:50-53)
+    on ONE frame pair (1/8 of the batch).  returns (Gq/s, seconds per call, threads)."""
+    from oracle import ref_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = torch.from_numpy(a[:1]); qry = torch.from_numpy(b[:1, :queries])
+    ref_torch.knn_topk(K_NN, ref[:, :2048], qry[:, :512])           # warm the thread pool
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ref_torch.knn_topk(K_NN, ref, qry)
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    return queries / t / 1e9, t, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's torch-CPU path on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from b200pc import synth
+    a, b = synth.batch_pairs(0, 1, NPTS)
+    # bounded sample per step: one pair of the batch of 8; shrink the query set for long runs
+    queries = NPTS if args.steps + args.warmup <= 40 else 4096
+    from oracle import ref_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = torch.from_numpy(a); qry = torch.from_numpy(b[:, :queries])
+    for _ in range(args.warmup):
+        ref_torch.knn_topk(K_NN, ref, qry)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref_torch.knn_topk(K_NN, ref, qry)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = queries / dt / 1e9
+    sample = "1 of the 8 frame pairs per step: %d queries x %d refs, k=%d (torch CPU: dense [N,S] matrix + topk(dim=1))" % (
+        queries, NPTS, K_NN)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def timed_steps(fn, steps, warmup, flush, stream_sync, barrier):
+    """W warm-ups, then K steps each bracketed by CUDA events on the current stream, an L2 flush
+    (outside the events) before every step; returns total seconds over the K steps."""
+    for _ in range(warmup):
+        flush(); fn()
+    stream_sync(); barrier()
+    evs = []
+    for _ in range(steps):
+        flush()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    stream_sync(); barrier()
+    return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3
+
+
+def extras(dev, a, b, flush):
+    """other kernels of the path at their BASELINE configs (C2 ball query, C3 FPS / gather /
+    three_interpolate, Chamfer), device-resident, 10 timed calls each."""
+    from b200pc import ops, pointnet2_utils as P
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+
+    def t(fn, n=10):
+        s = timed_steps(fn, n, 3, flush, torch.cuda.synchronize, lambda: None)
+        return s / n
+
+    ref = torch.from_numpy(a).to(dev); qry = torch.from_numpy(b).to(dev)
+    pairs = BATCH * NPTS * NPTS
+    s = t(lambda: P.query_ball_point(1.0, 32, ref, qry))
+    out["ball_query_c2"] = {"ms": s * 1e3, "gqueries_per_s": BATCH * NPTS / s / 1e9,
+                            "effective_tflops": pairs * FLOP_PER_PAIR / s / 1e12}
+    s = t(lambda: ops.knn_search(ref, qry, 16, ops.FORM_DIRECT, want_dist=True))
+    out["knn_points_direct_k16_c1x8"] = {"ms": s * 1e3, "tflops": pairs * FLOP_PER_PAIR / s / 1e12}
+
+    # C3: FPS 16384 -> 4096, gather C=128, three_interpolate C=128, batch 16
+    B3 = 16
+    a3 = np.concatenate([a, b], 0)[:B3]
+    xyz = torch.from_numpy(a3).to(dev)
+    start = torch.arange(B3, device=dev, dtype=torch.long) * 7
+    s = t(lambda: ops.fps(xyz, 4096, start), n=3)
+    out["fps_c3"] = {"ms": s * 1e3, "us_per_round": s * 1e6 / 4096, "clouds": B3}
+    s1 = t(lambda: ops.fps(xyz[:1], 1024, start[:1]), n=3)
+    out["fps_16384_to_1024_b1"] = {"ms": s1 * 1e3, "us_per_round": s1 * 1e6 / 1024}
+    fidx = ops.fps(xyz, 4096, start)
+    feats = torch.randn(B3, NPTS, 128, device=dev)
+    s = t(lambda: P.index_points(feats, fidx))
+    gbytes = B3 * 4096 * (128 * 4 * 2 + 8)
+    out["index_points_c3"] = {"ms": s * 1e3, "gb_per_s": gbytes / s / 1e9, "hbm_frac": gbytes / s / 1e9 / hbm,
+                              "algorithmic_bytes": gbytes}
+    known = P.index_points(xyz, fidx)
+    sfeat = P.index_points(feats, fidx)
+    s = t(lambda: P.three_nn_weights(xyz, known))
+    out["three_nn_c3"] = {"ms": s * 1e3, "tflops": B3 * NPTS * 4096 * FLOP_PER_PAIR / s / 1e12}
+    _, i3, w3 = P.three_nn_weights(xyz, known)
+    s = t(lambda: P.three_interpolate(sfeat, i3, w3))
+    ibytes = B3 * NPTS * 128 * 4 + B3 * 4096 * 128 * 4 + B3 * NPTS * (24 + 12)
+    out["three_interpolate_c3"] = {"ms": s * 1e3, "gb_per_s": ibytes / s / 1e9, "hbm_frac": ibytes / s / 1e9 / hbm,
+                                   "algorithmic_bytes": ibytes}
+    # Chamfer, C4 per-GPU share: 4 pairs x 8192 points
+    x = ref[:4, :8192].contiguous(); y = qry[:4, :8192].contiguous()
+    s = t(lambda: ops.chamfer(x, y))
+    out["chamfer_c4_share"] = {"ms": s * 1e3, "tflops": 2 * 4 * 8192 * 8192 * FLOP_PER_PAIR / s / 1e12}
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    from b200pc import ops, pointnet2_utils as P, synth, _lib
+    _lib.load()                                     # fail loudly if the native library is missing
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # every rank owns its own 8 frame pairs (weak scaling, batch sharding: no exchange in the path)
+    a, b = synth.batch_pairs(rank * BATCH, BATCH, NPTS)
+    ref = torch.from_numpy(a).to(dev); qry = torch.from_numpy(b).to(dev)
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    # ---- device-resident value --------------------------------------------------------------
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_id = str(local)
+    sampler = ClockSampler(gpu_id)
+    if rank == 0:
+        sampler.start()
+    ops.launch_count = 0
+    secs = timed_steps(lambda: P.knn_point(K_NN, ref, qry), args.steps, args.warmup, flush, torch.cuda.synchronize, barrier)
+    abi_calls = ops.launch_count
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([secs], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    secs_max = float(tmax.item())
+    queries_per_step = BATCH * NPTS * world
+    value = queries_per_step * args.steps / secs_max / 1e9
+
+    # ---- end to end: pinned host inputs -> H2D -> knn_point -> D2H of the indices -------------
+    h_ref = torch.from_numpy(a).pin_memory(); h_qry = torch.from_numpy(b).pin_memory()
+    h_out = torch.empty(BATCH, NPTS, K_NN, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        d_ref = h_ref.to(dev, non_blocking=True); d_qry = h_qry.to(dev, non_blocking=True)
+        h_out.copy_(P.knn_point(K_NN, d_ref, d_qry), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    esecs = timed_steps(e2e_step, e2e_steps, 3, flush, torch.cuda.synchronize, barrier)
+    et = torch.tensor([esecs], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = queries_per_step * e2e_steps / float(et.item()) / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (search_kernel): FP32 CUDA-core pipe -----------------
+    per_launch_s = secs / args.steps                       # pack_refs (~2 us) + search kernel, this rank
+    pairs = BATCH * NPTS * NPTS
+    achieved = pairs * FLOP_PER_PAIR / per_launch_s / 1e12
+    try:
+        fma_tf, fma_ms = ops.fma_peak(1 << 15)
+    except Exception as e:  # pragma: no cover
+        fma_tf, fma_ms = None, None
+    peak = fma_tf if fma_tf else FP32_NOMINAL_TFLOPS
+    roofline = {"bound": "fp32_cuda_core", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": "b200pc_fma_peak FFMA2 micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)"
+                if fma_tf else "nominal",
+                "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": achieved / FP32_NOMINAL_TFLOPS,
+                "algorithmic": "8 FLOP per (query, ref) pair x %d pairs per launch" % pairs,
+                "note": "K=3 contraction on FP32 CUDA cores (tensor cores would break the rounding parity); the "
+                        "contract's enum is hbm|tensor, this kernel is neither"}
+
+    # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
+    cval, csec, cthreads = cpu_reference_knn(a, b, reps=3)
+    cpu_baseline = {"value": cval, "unit": UNIT, "cores": cthreads, "kind": "port",
+                    "sample": "1 of the 8 frame pairs (16384 q x 16384 refs, k=16), median of 3; %.2f s per call" % csec}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "256 MB buffer rewritten before every timed step (L2 flush)",
+                       "parallelism": "batch-sharded, %d x 8 frame pairs, no data-path collective" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_ref.numel() * 4 + h_qry.numel() * 4),
+                    "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": e2e_steps},
+            # pack_refs_kernel + search_kernel per knn_point call (no ref split at C2), timed steps only
+            "gpu_launches": int(args.steps * 2), "abi_calls_incl_warmup": int(abi_calls),
+            "roofline": roofline, "cpu_baseline": cpu_baseline}
+    if args.extras and world == 1:
+        try:
+            line["extra"] = extras(dev, a, b, flush)
+        except Exception as e:  # pragma: no cover
+            line["extra"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

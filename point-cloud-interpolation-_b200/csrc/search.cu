@@ -34,7 +34,7 @@ namespace b200pc {
 
 constexpr int TILE = 512;                  // refs per shared-memory tile
 constexpr int TILE_BYTES = TILE * 16;      // 8 KB
-constexpr int STAGES = 4;                  // ring depth
+constexpr int STAGES = 3;                  // ring depth
 constexpr int CHUNK = 8;                   // refs per threshold test
 constexpr int CHUNKS_PER_TILE = TILE / CHUNK;
 constexpr int MAX_SPLIT = 32;
@@ -143,21 +143,75 @@ struct SearchArgs {
     int *part_cnt;         // [B][S][n_split]     (ball partial counts)
 };
 
-template <int FORM, int MODE, int Q, int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs P) {
-    constexpr int NCT = NCW * 32;   // consumer threads
-    constexpr int QPB = NCT * Q;    // queries per block
+// Order-preserving map fp32 -> u32 (negative expanded-form distances included), so that a
+// 64-bit key (map(d) << 32 | index) realises the total order (distance, index) with one compare.
+__device__ __forceinline__ uint32_t order_key(float d) {
+    const uint32_t b = __float_as_uint(d);
+    return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+constexpr unsigned long long HEAP_SENTINEL = 0xFF800000FFFFFFFFull;  // (+inf, max index)
+
+// max-heap of `n` 64-bit keys, element e of this query at heap[e * stride]; put `nk` at the root
+// and sift it down.  Depth is ceil(log2 n): every lane of a warp runs the same short loop.
+__device__ __forceinline__ void heap_sift_root(unsigned long long *heap, int stride, int n, unsigned long long nk) {
+    int pos = 0;
+    while (true) {
+        const int l = 2 * pos + 1;
+        if (l >= n) break;
+        int c = l;
+        unsigned long long kc = heap[l * stride];
+        if (l + 1 < n) {
+            const unsigned long long kr = heap[(l + 1) * stride];
+            if (kr > kc) { kc = kr; c = l + 1; }
+        }
+        if (kc <= nk) break;
+        heap[pos * stride] = kc;
+        pos = c;
+    }
+    heap[pos * stride] = nk;
+}
+
+constexpr int CAND_CAP = 32;  // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a sub-tile
+
+template <int FORM>
+__device__ __forceinline__ float tile_dist(const float4 *tp, int off, const QueryConst &q) {
+    float lo, hi;
+    unpack2(pair_dist<FORM>(tp[off & ~1], tp[(off & ~1) + 1], q), lo, hi);   // same packed arithmetic as the hot loop
+    return (off & 1) ? hi : lo;
+}
+
+constexpr int MAX_WARPS = 16;
+
+// Every warp is a consumer; there is no dedicated producer warp.  The ring is refilled by whichever
+// warp happens to release a stage LAST: after arriving on the stage's "empty" barrier each warp
+// probes it once (no spinning) and, if the phase is complete, claims the refill with a shared-memory
+// compare-and-swap and issues the bulk copy.  blockDim.x = warps * 32 is a RUNTIME value so that the
+// planner can size the grid as whole waves of resident CTAs.
+template <int FORM, int MODE, int Q>
+__global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs P) {
+    const int NCW = (int)(blockDim.x >> 5);       // warps
+    const int NCT = NCW * 32;                     // threads
+    const int QPB = NCT * Q;                      // queries per block
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem[];
     const float4 *tiles = reinterpret_cast<const float4 *>(smem);
     const uint32_t bar_base = smem_u32(smem + STAGES * TILE_BYTES);   // full[s] at +8s, empty[s] at +8(STAGES+s)
-    float *list_d = reinterpret_cast<float *>(smem + STAGES * TILE_BYTES + BAR_BYTES);
-    int *list_i = reinterpret_cast<int *>(list_d + (MODE == MODE_TOPK ? (size_t)P.k * QPB : 0));
+    int *issued = reinterpret_cast<int *>(smem + STAGES * TILE_BYTES + 8 * 2 * STAGES);   // tiles issued so far
+    // top-k: heap [k][QPB] u64, then candidate buffer [CAND_CAP][QPB] u16.   ball: list [k][QPB] u32
+    unsigned long long *heap_all = reinterpret_cast<unsigned long long *>(smem + STAGES * TILE_BYTES + BAR_BYTES);
+    unsigned short *cand_all = reinterpret_cast<unsigned short *>(heap_all + (size_t)P.k * QPB);
+    int *list_all = reinterpret_cast<int *>(heap_all);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int b = blockIdx.y, split = blockIdx.z;
     const int tile0 = split * P.tiles_per_split;
     const int tile1 = min(tile0 + P.tiles_per_split, P.n_pad / TILE);
     const int ntiles = tile1 - tile0;
+    const int k = P.k;
+    const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * P.n_pad + (size_t)tile0 * TILE) * 16;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -166,24 +220,15 @@ __global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs
             mbar_init(bar_base + 8 * (STAGES + s), NCW);
         }
         mbar_fence_init();
+        const int pre = ntiles < STAGES ? ntiles : STAGES;
+        for (int t = 0; t < pre; ++t) {
+            mbar_expect_tx(bar_base + 8 * t, TILE_BYTES);
+            bulk_g2s(smem_u32(smem + t * TILE_BYTES), src + (size_t)t * TILE_BYTES, TILE_BYTES, bar_base + 8 * t);
+        }
+        *issued = pre;
     }
     __syncthreads();
 
-    if (warp == NCW) {
-        // ---------------- TMA producer: one lane streams the tiles of this split ----------------
-        if (lane == 0) {
-            const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * P.n_pad + (size_t)tile0 * TILE) * 16;
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % STAGES;
-                if (t >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((t / STAGES) & 1) ^ 1);
-                mbar_expect_tx(bar_base + 8 * s, TILE_BYTES);
-                bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)t * TILE_BYTES, TILE_BYTES, bar_base + 8 * s);
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
     const int ct = threadIdx.x;  // 0 .. NCT-1
     QueryConst qc[Q];
     float tau[Q];
@@ -200,10 +245,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs
         cnt[j] = 0;
         if (MODE == MODE_TOPK) {
             tau[j] = CUDART_INF_F;
-            for (int s = 0; s < P.k; ++s) {
-                list_d[s * QPB + j * NCT + ct] = CUDART_INF_F;
-                list_i[s * QPB + j * NCT + ct] = 0;
-            }
+            for (int e = 0; e < k; ++e) heap_all[e * QPB + j * NCT + ct] = HEAP_SENTINEL;
         } else {
             tau[j] = P.r2;
         }
@@ -217,107 +259,165 @@ __global__ void __launch_bounds__((NCW + 1) * 32) search_kernel(const SearchArgs
 
         int c = 0;
         while (c < CHUNKS_PER_TILE) {
-            // warm-up (first tile of the split only): drain after 2,2,4,8,16 chunks so that tau
-            // tightens quickly; afterwards every 32 chunks (the width of the hit mask).
-            int nch = 32;
-            if (t == 0 && c < 32) nch = c < 2 ? 2 : c;
+            // warm-up (first tile of the split only): drain after 2,2,4,8,16,32 chunks so that tau
+            // tightens quickly; afterwards once per tile (64 chunks, two 32-bit hit masks).
+            int nch = CHUNKS_PER_TILE;
+            if (t == 0) nch = c < 2 ? 2 : (c < 32 ? c : 32);
             if (nch > CHUNKS_PER_TILE - c) nch = CHUNKS_PER_TILE - c;
 
-            uint32_t mask[Q];
+            // ---- hot loop: distance + half a min per pair, one compare per chunk, no branches ----
+            uint32_t mask[Q][2];
 #pragma unroll
-            for (int j = 0; j < Q; ++j) mask[j] = 0u;
-            uint32_t bit = 1u;
+            for (int j = 0; j < Q; ++j) { mask[j][0] = 0u; mask[j][1] = 0u; }
             const float4 *cp = tp + c * CHUNK;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
+                uint32_t bit = 1u;
 #pragma unroll 2
-            for (int cc = 0; cc < nch; ++cc, bit <<= 1, cp += CHUNK) {
-                float4 A[4], Bv[4];
+                for (int cc = 0; cc < n_here; ++cc, bit <<= 1, cp += CHUNK) {
+                    float4 A[4], Bv[4];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) { A[p] = cp[2 * p]; Bv[p] = cp[2 * p + 1]; }
+                    for (int p = 0; p < 4; ++p) { A[p] = cp[2 * p]; Bv[p] = cp[2 * p + 1]; }
 #pragma unroll
-                for (int j = 0; j < Q; ++j) {
-                    const float m = chunk_min<FORM>(A, Bv, qc[j]);
-                    const bool hit = MODE == MODE_TOPK ? (m < tau[j]) : (m <= tau[j]);
-                    if (hit) mask[j] |= bit;
+                    for (int j = 0; j < Q; ++j) {
+                        const float m = chunk_min<FORM>(A, Bv, qc[j]);
+                        const bool hit = MODE == MODE_TOPK ? (m < tau[j]) : (m <= tau[j]);
+                        if (hit) mask[j][half] |= bit;
+                    }
                 }
             }
 
-            // ---- drain: revisit hit chunks in index order, exact same arithmetic ----
+            // ---- drain, warp-synchronous so that the lanes' slow work overlaps instead of serialising ----
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
-                uint32_t m = mask[j];
+                uint32_t m0 = mask[j][0], m1 = mask[j][1];
                 const int slot = j * NCT + ct;
-                while (m) {
-                    const int cc = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float4 *dp = tp + (c + cc) * CHUNK;
-                    const int ref0 = tile_ref0 + (c + cc) * CHUNK;
-#pragma unroll 1
-                    for (int p = 0; p < 4; ++p) {
-                        float dd[2];
-                        unpack2(pair_dist<FORM>(dp[2 * p], dp[2 * p + 1], qc[j]), dd[0], dd[1]);
+                if (MODE == MODE_TOPK) {
+                    unsigned long long *heap = heap_all + slot;
+                    unsigned short *cand = cand_all + slot;
+                    while (__any_sync(FULL, (m0 | m1) != 0u)) {
+                        // phase 1: every lane revisits its r-th hit chunk; the chunk's candidates (d < stale tau)
+                        // are only recorded, as ONE entry (chunk << 8 | 8-bit mask), at most CAND_CAP per pass.
+                        int nc = 0;
+                        while (__any_sync(FULL, (m0 | m1) != 0u && nc < CAND_CAP)) {
+                            if ((m0 | m1) != 0u && nc < CAND_CAP) {
+                                int cc;
+                                if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
+                                else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+                                const float4 *dp = tp + (c + cc) * CHUNK;
+                                float d[8];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float d = dd[h];
-                            const int ri = ref0 + 2 * p + h;
-                            if (MODE == MODE_TOPK) {
+                                for (int p = 0; p < 4; ++p) unpack2(pair_dist<FORM>(dp[2 * p], dp[2 * p + 1], qc[j]), d[2 * p], d[2 * p + 1]);
+                                uint32_t cm = 0u;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) cm |= (d[i] < tau[j]) ? (1u << i) : 0u;
+                                if (cm != 0u) { cand[nc * QPB] = (unsigned short)((cc << 8) | cm); ++nc; }
+                            }
+                        }
+                        // phase 2: all lanes insert their next candidate together (index order is preserved)
+                        uint32_t cur = 0u;
+                        int e = 0, base = 0;
+                        while (true) {
+                            if (cur == 0u && e < nc) {
+                                const uint32_t v = cand[e * QPB];
+                                ++e;
+                                cur = v & 0xffu;
+                                base = (c + (int)(v >> 8)) * CHUNK;
+                            }
+                            if (!__any_sync(FULL, cur != 0u)) break;
+                            if (cur != 0u) {
+                                const int off = base + __ffs(cur) - 1;
+                                cur &= cur - 1;
+                                const float d = tile_dist<FORM>(tp, off, qc[j]);
                                 if (d < tau[j]) {
-                                    int pos = P.k - 1;
-                                    while (pos > 0) {
-                                        const float pd = list_d[(pos - 1) * QPB + slot];
-                                        if (!(pd > d)) break;
-                                        list_d[pos * QPB + slot] = pd;
-                                        list_i[pos * QPB + slot] = list_i[(pos - 1) * QPB + slot];
-                                        --pos;
-                                    }
-                                    list_d[pos * QPB + slot] = d;
-                                    list_i[pos * QPB + slot] = ri;
-                                    tau[j] = list_d[(P.k - 1) * QPB + slot];
-                                }
-                            } else {
-                                if (d <= tau[j]) {
-                                    list_i[cnt[j] * QPB + slot] = ri;
-                                    if (++cnt[j] == P.k) { tau[j] = -CUDART_INF_F; m = 0u; }
+                                    heap_sift_root(heap, QPB, k, ((unsigned long long)order_key(d) << 32) | (uint32_t)(tile_ref0 + off));
+                                    tau[j] = key_to_float((uint32_t)(heap[0] >> 32));
                                 }
                             }
+                        }
+                    }
+                } else {
+                    int *list = list_all + slot;
+                    while (__any_sync(FULL, (m0 | m1) != 0u)) {
+                        if ((m0 | m1) != 0u) {
+                            int cc;
+                            if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
+                            else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+                            const int off0 = (c + cc) * CHUNK;
+                            const float4 *dp = tp + off0;
+                            float d[8];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) unpack2(pair_dist<FORM>(dp[2 * p], dp[2 * p + 1], qc[j]), d[2 * p], d[2 * p + 1]);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (d[i] <= tau[j] && cnt[j] < k) { list[cnt[j] * QPB] = tile_ref0 + off0 + i; ++cnt[j]; }
+                            if (cnt[j] == k) { tau[j] = -CUDART_INF_F; m0 = 0u; m1 = 0u; }   // this query is complete
                         }
                     }
                 }
             }
             c += nch;
         }
+
+        // ---- release the stage; the warp that completes the release refills it ----
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
+        if (lane == 0) {
+            const uint32_t ebar = bar_base + 8 * (STAGES + s);
+            mbar_arrive(ebar);
+            const int nxt = t + STAGES;                 // the tile that will reuse this stage
+            if (nxt < ntiles && mbar_test(ebar, (t / STAGES) & 1)) {
+                if (atomicCAS(issued, nxt, nxt + 1) == nxt) {
+                    mbar_expect_tx(bar_base + 8 * s, TILE_BYTES);
+                    bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)nxt * TILE_BYTES, TILE_BYTES, bar_base + 8 * s);
+                }
+            }
+        }
     }
 
     // ---------------- results ----------------
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         const int qi = blockIdx.x * QPB + j * NCT + ct;
-        if (qi >= P.S) continue;
         const int slot = j * NCT + ct;
+        if (MODE == MODE_TOPK) {
+            // in-place heapsort: ascending (distance, index) order
+            unsigned long long *heap = heap_all + slot;
+            for (int n = k; n > 1; --n) {
+                const unsigned long long top = heap[0];
+                const unsigned long long last = heap[(n - 1) * QPB];
+                heap_sift_root(heap, QPB, n - 1, last);
+                heap[(n - 1) * QPB] = top;
+            }
+        }
+        if (qi >= P.S) continue;
         const size_t row = (size_t)b * P.S + qi;
         if (P.n_split == 1) {
-            int64_t *io = P.idx_out ? P.idx_out + row * P.k : nullptr;
+            int64_t *io = P.idx_out ? P.idx_out + row * k : nullptr;
             if (MODE == MODE_TOPK) {
-                float *dout = P.dist_out ? P.dist_out + row * P.k : nullptr;
-                for (int s = 0; s < P.k; ++s) {
-                    if (io) io[s] = list_i[s * QPB + slot];
-                    if (dout) dout[s] = list_d[s * QPB + slot];
+                float *dout = P.dist_out ? P.dist_out + row * k : nullptr;
+                for (int e = 0; e < k; ++e) {
+                    const unsigned long long key = heap_all[e * QPB + slot];
+                    if (io) io[e] = (int64_t)(uint32_t)key;
+                    if (dout) dout[e] = key_to_float((uint32_t)(key >> 32));
                 }
             } else {
-                const int first = cnt[j] > 0 ? list_i[slot] : P.N;
-                for (int s = 0; s < P.k; ++s) io[s] = s < cnt[j] ? list_i[s * QPB + slot] : first;
+                const int *list = list_all + slot;
+                const int first = cnt[j] > 0 ? list[0] : P.N;
+                for (int e = 0; e < k; ++e) io[e] = e < cnt[j] ? list[e * QPB] : first;
             }
         } else {
-            const size_t prow = (row * P.n_split + split) * P.k;
+            const size_t prow = (row * P.n_split + split) * k;
             if (MODE == MODE_TOPK) {
-                for (int s = 0; s < P.k; ++s) {
-                    P.part_d[prow + s] = list_d[s * QPB + slot];
-                    P.part_i[prow + s] = list_i[s * QPB + slot];
+                for (int e = 0; e < k; ++e) {
+                    const unsigned long long key = heap_all[e * QPB + slot];
+                    P.part_d[prow + e] = key_to_float((uint32_t)(key >> 32));
+                    P.part_i[prow + e] = (int)(uint32_t)key;
                 }
             } else {
+                const int *list = list_all + slot;
                 P.part_cnt[row * P.n_split + split] = cnt[j];
-                for (int s = 0; s < cnt[j]; ++s) P.part_i[prow + s] = list_i[s * QPB + slot];
+                for (int e = 0; e < cnt[j]; ++e) P.part_i[prow + e] = list[e * QPB];
             }
         }
     }
@@ -369,51 +469,75 @@ __global__ void merge_ball_kernel(const int *__restrict__ part_i, const int *__r
 // ---------------------------------------------------------------------------------------------
 // 5. planning + launch
 // ---------------------------------------------------------------------------------------------
-static size_t list_bytes(int k, int qpb, int mode) { return (size_t)k * qpb * (mode == MODE_TOPK ? 8 : 4); }
+// per-query shared-memory bytes.  top-k: u64 heap [k] + u16 candidate buffer [CAND_CAP];  ball: u32 list [nsample]
+static size_t query_bytes(int k, int mode) { return mode == MODE_TOPK ? (size_t)k * 8 + (size_t)CAND_CAP * 2 : (size_t)k * 4; }
 static const size_t kMaxSmem = 227 * 1024;
+static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 
+// Choose {queries per thread, consumer warps, ref split} so that the grid is (close to) a whole
+// number of waves of resident CTAs: CTA count = B * ceil(S / q_per_block) * n_split against
+// slots = SMs * CTAs-per-SM.  Among the candidates the one with the best wave efficiency wins;
+// ties go to more resident warps, then to Q=2 (half the shared-memory loads per pair).
 bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     const int sms = sm_count();
-    // candidate CTA shapes, largest first: {Q, consumer warps}
-    static const int shapes[][2] = {{2, 8}, {2, 4}, {1, 4}, {1, 2}};
-    const size_t fixed = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
-    int pick = -1;
-    for (int i = 0; i < 4; ++i) {
-        const int qpb = shapes[i][0] * shapes[i][1] * 32;
-        // keep at least two CTAs per SM resident while the lists fit
-        if (fixed + list_bytes(k, qpb, mode) <= kMaxSmem / 2 || i == 3) {
-            if (fixed + list_bytes(k, qpb, mode) > kMaxSmem) return false;
-            pick = i;
-            break;
-        }
-    }
-    // too few CTAs to occupy the machine: shrink the CTA first (more CTAs), then split the refs
-    while (pick < 3) {
-        const int qpb = shapes[pick][0] * shapes[pick][1] * 32;
-        const long ctas = (long)((S + qpb - 1) / qpb) * B;
-        if (ctas >= 2L * sms) break;
-        ++pick;
-    }
-    // tuning / debugging overrides (not part of the ABI): B200PC_FORCE_SHAPE=0..3, B200PC_FORCE_SPLIT=n
-    if (const char *e = getenv("B200PC_FORCE_SHAPE")) {
-        const int f = atoi(e);
-        if (f >= 0 && f < 4 && fixed + list_bytes(k, shapes[f][0] * shapes[f][1] * 32, mode) <= kMaxSmem) pick = f;
-    }
-    pl->q_per_thread = shapes[pick][0];
-    pl->consumer_warps = shapes[pick][1];
-    pl->q_per_block = shapes[pick][0] * shapes[pick][1] * 32;
+    const size_t qb = query_bytes(k, mode);
+    if (kFixedSmem + 32 * qb > kMaxSmem) return false;   // not even one warp of queries fits
     pl->n_pad = (int)align_up((size_t)N, TILE);
     pl->n_tiles = pl->n_pad / TILE;
-    const long ctas = (long)((S + pl->q_per_block - 1) / pl->q_per_block) * B;
-    int want = (int)((2L * sms + ctas - 1) / ctas);
-    if (want < 1) want = 1;
-    if (want > MAX_SPLIT) want = MAX_SPLIT;
-    if (const char *e = getenv("B200PC_FORCE_SPLIT")) { const int f = atoi(e); if (f >= 1) want = f; }
-    if (want > MAX_SPLIT) want = MAX_SPLIT;
-    if (want > pl->n_tiles) want = pl->n_tiles;
-    pl->tiles_per_split = (pl->n_tiles + want - 1) / want;
+
+    int force_q = 0, force_w = 0, force_split = 0;   // tuning / debugging overrides (not part of the ABI)
+    if (const char *e = getenv("B200PC_FORCE_Q")) force_q = atoi(e);
+    if (const char *e = getenv("B200PC_FORCE_WARPS")) force_w = atoi(e);
+    if (const char *e = getenv("B200PC_FORCE_SPLIT")) force_split = atoi(e);
+
+    double best_score = -1.0;
+    int best_q = 1, best_w = 1, best_split = 1;
+    for (int q = 2; q >= 1; --q) {
+        if (force_q && q != force_q) continue;
+        for (int c = 1; c <= 8; ++c) {                       // target CTAs per SM
+            const size_t budget = kMaxSmem / c - 1024;          // ~1 KB per resident CTA is reserved by the system
+            if (budget <= kFixedSmem + 32 * q * qb) continue;
+            int wmax = (int)((budget - kFixedSmem) / (32 * q * qb));
+            if (wmax > MAX_WARPS) wmax = MAX_WARPS;
+            const long slots = (long)sms * c;
+            // queries per CTA if the S queries of each batch item are spread over the slots
+            long ipb = slots / B;                            // items (CTAs) per batch item, one wave
+            if (ipb < 1) ipb = 1;
+            int w = (int)((((long)S + ipb - 1) / ipb + 32 * q - 1) / (32 * q));
+            if (w < 1) w = 1;
+            if (w > wmax) w = wmax;
+            if (force_w) w = force_w > wmax ? wmax : force_w;
+            // register file: 64K registers per SM, ~88 (Q=2) / ~64 (Q=1) per thread
+            if ((long)w * 32 * c * (q == 2 ? 88 : 64) > 65536) continue;
+            const long items = (long)B * (((long)S + 32L * q * w - 1) / (32L * q * w));
+            // too few CTAs for the machine: split the ref range (partial lists are merged afterwards)
+            int split = 1;
+            if (items * 2 <= slots) {
+                split = (int)(slots / items);
+                if (split > MAX_SPLIT) split = MAX_SPLIT;
+                if (split > pl->n_tiles) split = pl->n_tiles;
+                if (split < 1) split = 1;
+            }
+            if (force_split) split = force_split > pl->n_tiles ? pl->n_tiles : (force_split > MAX_SPLIT ? MAX_SPLIT : force_split);
+            const int tps = (pl->n_tiles + split - 1) / split;
+            split = (pl->n_tiles + tps - 1) / tps;
+            const long ctas = items * split;
+            const long waves = (ctas + slots - 1) / slots;
+            const double wave_eff = (double)ctas / (double)(waves * slots);
+            const double pad_eff = (double)B * S / ((double)items * 32 * q * w);
+            const double warps = (double)c * w;
+            const double occ = warps >= 12 ? 1.0 : 0.55 + 0.45 * warps / 12.0;   // few resident warps hide latency badly
+            const double split_cost = split > 1 ? 0.9 : 1.0;
+            const double score = wave_eff * pad_eff * occ * split_cost + 1e-3 * (q == 2) + 1e-4 * warps;
+            if (score > best_score) { best_score = score; best_q = q; best_w = w; best_split = split; }
+        }
+    }
+    pl->q_per_thread = best_q;
+    pl->consumer_warps = best_w;
+    pl->q_per_block = best_q * best_w * 32;
+    pl->tiles_per_split = (pl->n_tiles + best_split - 1) / best_split;
     pl->n_split = (pl->n_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
-    pl->smem_bytes = fixed + list_bytes(k, pl->q_per_block, mode);
+    pl->smem_bytes = kFixedSmem + (size_t)pl->q_per_block * qb;
     pl->packed_bytes = align_up((size_t)B * pl->n_pad * 16, 256);
     pl->part_bytes = 0;
     if (pl->n_split > 1) {
@@ -424,22 +548,20 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     return true;
 }
 
-template <int FORM, int MODE, int Q, int NCW>
+template <int FORM, int MODE, int Q>
 static int launch_one(const SearchArgs &a, const SearchPlan &pl, int B, cudaStream_t st) {
-    auto kern = search_kernel<FORM, MODE, Q, NCW>;
+    auto kern = search_kernel<FORM, MODE, Q>;
     B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
     dim3 grid((a.S + pl.q_per_block - 1) / pl.q_per_block, B, pl.n_split);
-    kern<<<grid, (NCW + 1) * 32, pl.smem_bytes, st>>>(a);
+    kern<<<grid, pl.consumer_warps * 32, pl.smem_bytes, st>>>(a);
     B200PC_LAUNCH_CHECK();
     return B200PC_OK;
 }
 
 template <int FORM, int MODE>
 static int launch_shape(const SearchArgs &a, const SearchPlan &pl, int B, cudaStream_t st) {
-    if (pl.q_per_thread == 2 && pl.consumer_warps == 8) return launch_one<FORM, MODE, 2, 8>(a, pl, B, st);
-    if (pl.q_per_thread == 2 && pl.consumer_warps == 4) return launch_one<FORM, MODE, 2, 4>(a, pl, B, st);
-    if (pl.q_per_thread == 1 && pl.consumer_warps == 4) return launch_one<FORM, MODE, 1, 4>(a, pl, B, st);
-    return launch_one<FORM, MODE, 1, 2>(a, pl, B, st);
+    if (pl.q_per_thread == 2) return launch_one<FORM, MODE, 2>(a, pl, B, st);
+    return launch_one<FORM, MODE, 1>(a, pl, B, st);
 }
 
 static int run_search(const float *ref, const float *qry, int B, int N, int S, int k, int form, int mode, float r2,

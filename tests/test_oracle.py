@@ -1,0 +1,211 @@
+"""CPU tests: pin oracle/strict.c (and the torch port that bench.py times) against
+
+  (1) tests/golden/reference_outputs.npz -- outputs of the REAL reference executed in the build
+      container by tests/golden/make_golden.py;
+  (2) the real reference itself when /root/reference is present (build container only);
+  (3) each other.
+
+Index comparisons are tie-aware: torch's topk/sort are not index-stable,
+so rows containing exactly equal distances among the k+1 nearest are exempted from the
+index-equality check (their distance vectors must still agree bit for bit).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from b200pc import synth
+from oracle import ref_loader, ref_torch, strict
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+@pytest.fixture(scope="module")
+def pair100():
+    return synth.batch_pairs(100, 2, 4096)
+
+
+def tie_free_rows(ref, qry, k, form):
+    """rows whose k+1 smallest distances are pairwise distinct (indices are then unambiguous)."""
+    kk = min(k + 1, ref.shape[1])
+    _, d = strict.knn(ref, qry, kk, form)
+    return (np.diff(d, axis=-1) != 0).all(-1)
+
+
+# ---------------------------------------------------------------- golden vectors
+def test_golden_square_distance(pair100):
+    a, b = pair100
+    assert np.array_equal(bits(strict.square_distance(a[:, :96], b[:, :64])), bits(GOLD["sqdist_small"]))
+    assert np.array_equal(sha(strict.square_distance(a, b[:, :1024])), GOLD["sqdist_4096x1024_sha"])
+    assert np.array_equal(sha(strict.square_distance(a[:, :1024], b)), GOLD["sqdist_1024x4096_sha"])
+    assert np.array_equal(sha(strict.square_distance(a, b[:, :256])), GOLD["sqdist_permuted_sha"])
+
+
+def test_golden_fps(pair100):
+    a, _ = pair100
+    g = GOLD["fps_4096_512"]
+    assert np.array_equal(strict.farthest_point_sample(a, 512, g[:, 0]), g)
+    a16, _ = synth.batch_pairs(101, 1, 16384)
+    g = GOLD["fps_16384_1024"]
+    assert np.array_equal(strict.farthest_point_sample(a16, 1024, g[:, 0]), g)
+    dup = np.concatenate([a[:, :1500], a[:, :548]], 1)
+    g = GOLD["fps_dup_2048_700"]
+    assert np.array_equal(strict.farthest_point_sample(dup, 700, g[:, 0]), g)
+
+
+def test_golden_fps_start_comes_from_torch_cpu_rng():
+    # the reference draws torch.randint(0, N, (B,)) after manual_seed (Pointnet2Utils.py:76)
+    torch.manual_seed(3000)
+    assert np.array_equal(torch.randint(0, 4096, (2,), dtype=torch.long).numpy(), GOLD["fps_4096_512"][:, 0])
+
+
+@pytest.mark.parametrize("r,ns,nq", [(1.0, 32, 512), (0.5, 16, 512), (0.1, 16, 256), (4.0, 8, 64)])
+def test_golden_ball_query(pair100, r, ns, nq):
+    a, b = pair100
+    g = GOLD["ball_r%g_ns%d_q%d" % (r, ns, nq)]
+    assert np.array_equal(strict.query_ball_point(r, ns, a, b[:, :nq]), g)
+
+
+def test_golden_ball_query_self(pair100):
+    a, _ = pair100
+    assert np.array_equal(strict.query_ball_point(0.5, 16, a, a[:, ::8]), GOLD["ball_self_r0.5_ns16"])
+
+
+def test_golden_index_points():
+    rng = np.random.default_rng(5)
+    feats = rng.normal(size=(2, 4096, 24)).astype(np.float32)
+    idx = GOLD["gather_idx"].astype(np.int64)
+    assert np.array_equal(sha(strict.index_points(feats, idx)), GOLD["gather_out_sha"])
+
+
+@pytest.mark.parametrize("k,nq,nr", [(16, 512, 4096), (8, 256, 64), (64, 256, 256)])
+def test_golden_knn_group(pair100, k, nq, nr):
+    a, b = pair100
+    ref, qry = a[:, :nr].copy(), b[:, :nq].copy()
+    g = GOLD["knn_k%d_q%d_r%d" % (k, nq, nr)].astype(np.int64)
+    mine = strict.knn_point(k, ref, qry)
+    clean = tie_free_rows(ref, qry, k, strict.FORM_KNN)
+    assert clean.mean() > 0.9
+    assert np.array_equal(mine[clean], g[clean])
+    # rows with ties: same multiset of distances, bit for bit
+    full = strict.square_distance(ref, qry)                      # [B,N,S], refs are `src`
+    for bi, si in np.argwhere(~clean):
+        dg = np.sort(full[bi, g[bi, si], si]); dm = np.sort(full[bi, mine[bi, si], si])
+        assert np.array_equal(bits(dg), bits(dm))
+
+
+def test_golden_three_nn_variant_a(pair100):
+    a, _ = pair100
+    S, N = 64, 1024
+    dense = a[:, :N].copy(); sparse = a[:, :N:N // S][:, :S].copy()
+    d, idx = strict.three_nn(dense, sparse)
+    w = strict.three_weights(d, 0)
+    rows = GOLD["fp_a_weight_rows"]                              # [B,N,S] three non-zeros per row
+    mine = np.zeros_like(rows)
+    np.put_along_axis(mine, idx, w, axis=-1)
+    clean = tie_free_rows(sparse, dense, 3, strict.FORM_QFIRST)
+    assert clean.mean() > 0.95
+    assert np.array_equal((rows != 0)[clean], (mine != 0)[clean])            # same three neighbours
+    np.testing.assert_allclose(mine[clean], rows[clean], rtol=1e-5, atol=1e-7)
+    feat = GOLD["fp_a_feat"].transpose(0, 2, 1).copy()            # [B,S,C]
+    out = strict.three_interpolate(feat, idx, w).transpose(0, 2, 1)
+    np.testing.assert_allclose(out[:, :, clean[0] & clean[1]], GOLD["fp_a_out"][:, :, clean[0] & clean[1]], rtol=1e-5, atol=1e-6)
+
+
+def test_golden_three_nn_variant_b(pair100):
+    a, _ = pair100
+    S, N = 64, 1024
+    dense = a[:, :N].copy(); sparse = a[:, :N:N // S][:, :S].copy()
+    d, idx = strict.three_nn(dense, sparse)
+    w = strict.three_weights(d, 1)
+    feat = GOLD["fp_a_feat"].transpose(0, 2, 1).copy()
+    out = strict.three_interpolate(feat, idx, w).transpose(0, 2, 1)
+    clean = tie_free_rows(sparse, dense, 3, strict.FORM_QFIRST)
+    m = clean[0] & clean[1]
+    np.testing.assert_allclose(out[:, :, m], GOLD["fp_b_out"][:, :, m], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- torch port == strict oracle
+def test_torch_port_matches_strict(pair100):
+    a, b = pair100
+    A, B_ = torch.from_numpy(a[:, :2048]), torch.from_numpy(b[:, :512])
+    assert np.array_equal(bits(ref_torch.dense_sqdist(A, B_).numpy()), bits(strict.square_distance(a[:, :2048], b[:, :512])))
+    start = torch.tensor([3, 99])
+    assert np.array_equal(ref_torch.fps(A, 128, start).numpy(), strict.farthest_point_sample(a[:, :2048], 128, start.numpy()))
+    assert np.array_equal(ref_torch.ball(1.0, 32, A, B_).numpy(), strict.query_ball_point(1.0, 32, a[:, :2048], b[:, :512]))
+    clean = tie_free_rows(a[:, :2048], b[:, :512], 16, strict.FORM_KNN)
+    assert np.array_equal(ref_torch.knn_topk(16, A, B_).numpy()[clean], strict.knn_point(16, a[:, :2048], b[:, :512])[clean])
+    feat = torch.randn(2, 512, 16, generator=torch.Generator().manual_seed(1))
+    out, d, idx, w = ref_torch.three_nn_interp(A, B_, feat, variant=0)
+    sd, si = strict.three_nn(a[:, :2048], b[:, :512])
+    c3 = tie_free_rows(b[:, :512], a[:, :2048], 3, strict.FORM_QFIRST)
+    assert np.array_equal(idx.numpy()[c3], si[c3])
+    np.testing.assert_allclose(out.numpy()[c3], strict.three_interpolate(feat.numpy(), si, strict.three_weights(sd, 0))[c3], rtol=1e-5, atol=1e-6)
+
+
+def test_strict_knn_direct_and_chamfer_against_dense_float64():
+    a, b = synth.batch_pairs(7, 2, 600)
+    d64 = ((a[:, :, None, :].astype(np.float64) - b[:, None, :, :].astype(np.float64)) ** 2).sum(-1)
+    dist, idx = strict.knn_points(a, b, 4)
+    ref_sorted = np.sort(d64, axis=-1)[:, :, :4]
+    np.testing.assert_allclose(dist, ref_sorted, rtol=1e-5, atol=1e-6)
+    loss = strict.chamfer(a, b)[0]
+    ref_loss = (d64.min(2).mean(1) + d64.min(1).mean(1)).mean()
+    assert abs(loss - ref_loss) <= 1e-5 * ref_loss
+    tl = ref_torch.chamfer_dense(torch.from_numpy(a), torch.from_numpy(b)).item()
+    assert abs(tl - ref_loss) <= 1e-5 * ref_loss
+
+
+def test_strict_tie_rule_lowest_index():
+    pts = synth.grid_snapped(1, 1, 400, span=3)
+    q = synth.grid_snapped(2, 1, 50, span=3)
+    idx, d = strict.knn(pts, q, 8, strict.FORM_KNN)
+    full = strict.square_distance(pts, q)[0]                      # [N,S]
+    for s in range(50):
+        order = np.lexsort((np.arange(400), full[:, s]))[:8]      # by (distance, index)
+        assert np.array_equal(idx[0, s], order)
+
+
+def test_strict_edge_cases():
+    pts = np.random.default_rng(0).normal(size=(1, 5, 3)).astype(np.float32)
+    idx, _ = strict.knn(pts, pts, 5, 0)                           # k == N
+    assert sorted(idx[0, 0].tolist()) == [0, 1, 2, 3, 4]
+    out = strict.query_ball_point(0.01, 4, pts, pts + 100.0)      # all balls empty -> sentinel N
+    assert (out == 5).all()
+    with pytest.raises(IndexError):
+        strict.index_points(pts, np.array([[5]]))
+    assert strict.farthest_point_sample(pts, 5, np.array([2]))[0, 0] == 2
+
+
+# ---------------------------------------------------------------- real reference (container only)
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present (GPU box)")
+
+
+@needs_ref
+def test_real_reference_agrees_with_oracle_live():
+    R = ref_loader.pointnet2_utils()
+    a, b = synth.batch_pairs(200, 2, 1500)
+    A, B_ = torch.from_numpy(a), torch.from_numpy(b[:, :300])
+    assert np.array_equal(bits(R.square_distance(A, B_).numpy()), bits(strict.square_distance(a, b[:, :300])))
+    assert np.array_equal(R.query_ball_point(0.8, 16, A, B_).numpy(), strict.query_ball_point(0.8, 16, a, b[:, :300]))
+    torch.manual_seed(5)
+    f = R.farthest_point_sample(A, 200).numpy()
+    assert np.array_equal(f, strict.farthest_point_sample(a, 200, f[:, 0]))
+    idx = torch.from_numpy(f)
+    assert np.array_equal(R.index_points(A, idx).numpy(), strict.index_points(a, f))
+
+
+@needs_ref
+def test_real_reference_layers_import_with_stubs():
+    L = ref_loader.layers()
+    assert hasattr(L, "Group") and hasattr(L, "FeaturePropagation") and hasattr(L, "PointsFusion")
