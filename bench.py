@@ -218,6 +218,65 @@ def extras(dev, a, b, flush):
     return out
 
 
+def pointinet_inputs(pair, n, dev=None, pinned=False):
+    """one synthetic frame pair as PointINet inputs: points [1,4,n] (xyz + intensity), zero features, t=0.5"""
+    from b200pc import synth
+    a, b = synth.frame_pair(pair, n)
+    g = torch.Generator().manual_seed(pair)
+    mk = lambda f: torch.cat([torch.from_numpy(f).t(), torch.rand(1, n, generator=g)], 0).unsqueeze(0).contiguous()
+    ts = [mk(a), mk(b), torch.zeros(1, 3, n), torch.zeros(1, 3, n), torch.tensor([0.5])]
+    if pinned:
+        ts = [x.pin_memory() for x in ts]
+    if dev is not None:
+        ts = [x.to(dev) for x in ts]
+    return ts
+
+
+def pointinet_bench(dev, rank, steps, flush, barrier, dist):
+    """BASELINE metric (i): PointINet interpolated frames/s at 16384 points, batch 1, t=0.5, random
+    weights (the reference ships none).  Every rank interpolates its own frame pairs.
+    returns (device-resident seconds/frame, host-buffer seconds/frame) as the max over ranks."""
+    from b200pc import pointinet
+    torch.manual_seed(0)
+    net = pointinet.PointINet().eval().to(dev)
+    dev_in = pointinet_inputs(100 + rank, NPTS, dev=dev)
+    host_in = pointinet_inputs(100 + rank, NPTS, pinned=True)
+    host_out = torch.empty(1, 4, NPTS).pin_memory()
+
+    def resident():
+        with torch.no_grad():
+            net(*dev_in)
+
+    def hosted():
+        with torch.no_grad():
+            host_out.copy_(net(*[x.to(dev, non_blocking=True) for x in host_in]), non_blocking=True)
+
+    out = []
+    for fn in (resident, hosted):
+        torch.manual_seed(3000 + rank)
+        secs = timed_steps(fn, steps, 3, flush, torch.cuda.synchronize, barrier)
+        tm = torch.tensor([secs / steps], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        out.append(float(tm.item()))
+    return out[0], out[1]
+
+
+def pointinet_cpu_baseline():
+    """one PointINet forward with the reference's torch-CPU primitives (oracle.cpu_backend), all host threads"""
+    from b200pc import pointinet
+    from oracle import cpu_backend
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    net = pointinet.PointINet(backend=cpu_backend.make()).eval()
+    ins = pointinet_inputs(100, NPTS)
+    torch.manual_seed(3000)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        net(*ins)
+    return time.perf_counter() - t0, torch.get_num_threads()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -283,6 +342,15 @@ def main():
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = queries_per_step * e2e_steps / float(et.item()) / 1e9
 
+    # ---- metric (i): PointINet frames/s, every rank on its own frame pairs ----------------------
+    pn_dev = pn_host = None
+    if args.extras:
+        try:
+            pn_dev, pn_host = pointinet_bench(dev, rank, max(3, min(args.steps, 10)), flush, barrier, dist)
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                print("pointinet bench failed: %r" % (e,), file=sys.stderr)
+
     if rank != 0:
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
@@ -322,6 +390,17 @@ def main():
             # pack_refs_kernel + search_kernel per knn_point call (no ref split at C2), timed steps only
             "gpu_launches": int(args.steps * 2), "abi_calls_incl_warmup": int(abi_calls),
             "roofline": roofline, "cpu_baseline": cpu_baseline}
+    if pn_dev:
+        line["pointinet"] = {"metric": "pointinet_interp_frames_per_s", "workload": "C1: PointINet forward, 16384 points, batch 1 per GPU, t=0.5, random weights",
+                             "value": world / pn_dev, "e2e_value": world / pn_host, "unit": "frames/s", "ms_per_frame": pn_dev * 1e3,
+                             "ms_per_frame_e2e": pn_host * 1e3, "paper_rtx2060_frames_per_s": 4.9}
+        if world == 1:
+            try:
+                csec, cthr = pointinet_cpu_baseline()
+                line["pointinet"]["cpu_baseline"] = {"value": 1.0 / csec, "unit": "frames/s", "cores": cthr, "kind": "port",
+                                                     "sample": "one forward, %.1f s" % csec}
+            except Exception as e:  # pragma: no cover
+                line["pointinet"]["cpu_baseline"] = {"error": repr(e)}
     if args.extras and world == 1:
         try:
             line["extra"] = extras(dev, a, b, flush)

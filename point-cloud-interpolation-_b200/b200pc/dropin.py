@@ -48,9 +48,11 @@ def install_pytorch3d(force=False):
             return False
         except Exception:
             pass
-    _ensure_stub("pytorch3d")
-    _ensure_stub("pytorch3d.ops", knn_points=shim.knn_points, knn_gather=shim.knn_gather)
-    _ensure_stub("pytorch3d.loss", chamfer_distance=shim.chamfer_distance)
+    pkg = _ensure_stub("pytorch3d")
+    if not hasattr(pkg, "__path__"):
+        pkg.__path__ = []          # mark as a package so `import pytorch3d.ops` resolves through sys.modules
+    pkg.ops = _ensure_stub("pytorch3d.ops", knn_points=shim.knn_points, knn_gather=shim.knn_gather)
+    pkg.loss = _ensure_stub("pytorch3d.loss", chamfer_distance=shim.chamfer_distance)
     return True
 
 

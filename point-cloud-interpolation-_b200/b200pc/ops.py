@@ -164,6 +164,8 @@ def gather(points, idx):
     idx = _idx64(idx, points.device)
     B = points.shape[0]
     out_shape = tuple(idx.shape) + (points.shape[2],)
+    if points.shape[2] == 0 or idx.numel() == 0:      # nothing to move (e.g. clouds without extra channels)
+        return torch.empty(out_shape, dtype=torch.float32, device=points.device)
     idx_flat = idx.reshape(B, -1)
     if points.requires_grad and torch.is_grad_enabled():
         return _GatherFn.apply(points, idx_flat, out_shape)

@@ -32,7 +32,11 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
         raise NotImplementedError("b200pc.knn_points: only norm=2 (the reference's only use)")
     if p1.shape[-1] != 3 or p2.shape[-1] != 3:
         raise ValueError("b200pc.knn_points: points must be [B,P,3]")
-    K = min(int(K), p2.shape[1]) if p2.shape[1] > 0 else int(K)
+    K = min(int(K), p2.shape[1])
+    if K <= 0 or p1.shape[1] == 0:
+        B, P1 = p1.shape[0], p1.shape[1]
+        z = p1.new_zeros(B, P1, 0)
+        return _KNN(z, z.long(), p1.new_zeros(B, P1, 0, 3) if return_nn else None)
     idx, dists = ops.knn_search(p2.detach(), p1.detach(), K, ops.FORM_DIRECT, want_dist=True)
     nn = None
     grad = torch.is_grad_enabled() and (p1.requires_grad or p2.requires_grad)
