@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--extras", type=int, default=1, help="also time the other kernels of the path (rank 0)")
+    ap.add_argument("--ref-queries", type=int, default=0, help="(--impl reference) queries per step; 0 = automatic")
     return ap.parse_args()
 
 
@@ -127,6 +128,8 @@ def run_reference(args, rank, world):
     a, b = synth.batch_pairs(0, 1, NPTS)
     # bounded sample per step: one pair of the batch of 8; shrink the query set for long runs
     queries = NPTS if args.steps + args.warmup <= 40 else 4096
+    if args.ref_queries:
+        queries = args.ref_queries
     from oracle import ref_torch
     torch.set_num_threads(os.cpu_count() or 1)
     ref = torch.from_numpy(a); qry = torch.from_numpy(b[:, :queries])

@@ -1,0 +1,71 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes, a CPU stand-in for the search op."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from b200pc import dist as bdist, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 16384, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [bdist.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle import ref_torch
+    a, b = synth.batch_pairs(3, 2, 1500)
+    refs = torch.from_numpy(a); qry = torch.from_numpy(b[:, :701].copy())     # odd count -> ragged shards
+    full = ref_torch.knn_topk(8, refs, qry)
+    got = bdist.query_sharded(lambda s: ref_torch.knn_topk(8, refs, s), qry)
+    ok1 = torch.equal(got, full)
+    d_full, i_full = ref_torch.knn_points_dense(qry, refs, 4)
+    d, i = bdist.query_sharded(lambda s: ref_torch.knn_points_dense(s, refs, 4), qry)
+    ok2 = torch.equal(i, i_full) and torch.equal(d, d_full)
+    mine = bdist.batch_shard([refs, qry])
+    ok3 = mine[0].shape[0] == 1 and torch.equal(mine[0][0], refs[rank])
+    q.put((rank, ok1, ok2, ok3))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_query_sharded_all_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def test_bench_reference_arm_under_torchrun_world2():
+    """rank 0 alone measures and prints ONE json line; the other rank exits 0 without work."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--ref-queries", "512"]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "knn_point_gqueries_per_s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
