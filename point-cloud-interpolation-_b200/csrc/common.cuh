@@ -152,6 +152,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// ---- distributed shared memory (thread-block clusters) ----
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// 16-byte asynchronous store into a peer CTA's shared memory; the bytes are counted on the peer's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar_cluster)
+                 : "memory");
+}
+// wait with cluster-scope acquire: data written by peers with st.async is visible afterwards
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // streaming (no L1 allocate) 128-bit global accesses for the HBM-bound kernels
 // ---------------------------------------------------------------------------------------------

@@ -8,10 +8,11 @@
 //   * the update is packed fp32x2 math in the reference's exact rounding order
 //     d = ((dx*dx + dy*dy) + dz*dz), dx = x - cx, no FMA;
 //   * arg-max: min-dists are >= +0, so their bit patterns order like unsigned ints:
-//     REDUX.MAX per warp, one __syncthreads, REDUX again over the warp maxima; only the threads
-//     that hold the block maximum resolve the lowest index (shared atomicMin);
-//   * across CTAs: each CTA stores {max bits, index, centroid xyz} into every peer's shared
-//     memory (DSMEM), one cluster barrier per round, every thread then picks the winner locally.
+//     the pair (bits, ~index) is reduced as one key: two REDUX per warp, ONE __syncthreads per round,
+//     two REDUX over the warp keys (lowest index wins ties);
+//   * across CTAs: each CTA pushes {max bits, index, centroid xyz} into every peer's shared memory with
+//     st.async (DSMEM); the bytes complete on the receiver's mbarrier, so a round costs one DSMEM latency
+//     and no cluster-wide barrier or membar; every thread then picks the winner locally.
 // HBM traffic is N*12 bytes in and npoint*8 bytes out per cloud; the kernel is bound by the
 // barrier latency of a round, reported by bench.py as microseconds per round.
 #include <cooperative_groups.h>
@@ -46,9 +47,9 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
 
     extern __shared__ __align__(16) float fps_smem[];
     float *sx = fps_smem, *sy = sx + FPS_T * P, *sz = sy + FPS_T * P;
-    __shared__ unsigned int warp_max[FPS_WARPS];
-    __shared__ int cand[2];
+    __shared__ uint2 warp_key[2][FPS_WARPS];   // per-warp (max bits, ~index), double-buffered by round parity
     __shared__ FpsRecord rec[2][FPS_MAX_CLUSTER];
+    __shared__ __align__(8) unsigned long long xbar[2];   // receive barriers of the record exchange
 
     const float *cloud = xyz + (size_t)b * N * 3;
     float x[P], y[P], z[P], mind[P];
@@ -63,7 +64,10 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
         }
         sx[p * FPS_T + t] = x[p]; sy[p * FPS_T + t] = y[p]; sz[p * FPS_T + t] = z[p];
     }
-    if (t == 0) { cand[0] = INT_MAX; cand[1] = INT_MAX; }
+    if (t == 0) {
+        mbar_init(smem_u32(&xbar[0]), 1); mbar_init(smem_u32(&xbar[1]), 1);
+        mbar_fence_init();
+    }
     int far = (int)start[b];
     float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
     if (C > 1) cluster.sync(); else __syncthreads();
@@ -95,44 +99,47 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
             lmax = mind[0];
         }
 
-        // ---- block arg-max (first index) ----
-        const unsigned int lbits = __float_as_uint(lmax);
-        const unsigned int wbits = __reduce_max_sync(0xffffffffu, lbits);
-        if (lane == 0) warp_max[warp] = wbits;
-        __syncthreads();
-        const unsigned int cbits = __reduce_max_sync(0xffffffffu, warp_max[lane & (FPS_WARPS - 1)]);
-        if (lbits == cbits) {
-            int lp = 0;
+        // ---- block arg-max (first index) with ONE barrier: the pair (max bits, ~index) is reduced as a
+        // 64-bit key -- two REDUX per warp, one shared write per warp, one __syncthreads, two REDUX again.
+        int lp = 0;
 #pragma unroll
-            for (int p = P - 1; p >= 0; --p)
-                if (mind[p] == lmax) lp = p;
-            atomicMin(&cand[it & 1], cta_base + lp * FPS_T + t);
-        }
-        if (t == 0) cand[(it + 1) & 1] = INT_MAX;  // reset the other parity for the next round
+        for (int p = P - 1; p >= 0; --p)
+            if (mind[p] == lmax) lp = p;                       // first local point attaining the local max
+        const unsigned int lbits = __float_as_uint(lmax);
+        const unsigned int linv = 0xffffffffu - (unsigned int)(cta_base + lp * FPS_T + t);   // larger = lower index
+        unsigned int wbits = __reduce_max_sync(0xffffffffu, lbits);
+        unsigned int winv = __reduce_max_sync(0xffffffffu, lbits == wbits ? linv : 0u);
+        if (lane == 0) warp_key[it & 1][warp] = make_uint2(wbits, winv);
         __syncthreads();
-        const int ci = cand[it & 1];
+        const uint2 wk = warp_key[it & 1][lane & (FPS_WARPS - 1)];
+        const unsigned int cbits = __reduce_max_sync(0xffffffffu, wk.x);
+        const unsigned int cinv = __reduce_max_sync(0xffffffffu, wk.x == cbits ? wk.y : 0u);
+        const int ci = (int)(0xffffffffu - cinv);
         const int cl = ci - cta_base;
 
         if (C == 1) {
             far = ci;
             cx = sx[cl]; cy = sy[cl]; cz = sz[cl];
         } else {
-            // ---- cluster arg-max: all-to-all of one 32-byte record through DSMEM ----
+            // ---- cluster arg-max: all-to-all of one 32-byte record through DSMEM.  Each record is pushed
+            // with st.async, which completes bytes on the RECEIVER's mbarrier: no cluster-wide barrier and
+            // no membar per round, only the DSMEM latency.  Slots / barriers alternate with round parity.
+            const int par = it & 1;
+            const uint32_t my_bar = smem_u32(&xbar[par]);
+            if (t == 0) mbar_expect_tx(my_bar, (uint32_t)(C * sizeof(FpsRecord)));   // C records will land here
             if (t < C) {
-                FpsRecord r;
-                r.bits = cbits; r.idx = ci; r.x = sx[cl]; r.y = sy[cl]; r.z = sz[cl];
-                r.pad[0] = r.pad[1] = r.pad[2] = 0;
-                FpsRecord *peer = cluster.map_shared_rank(&rec[it & 1][rank], t);
-                *reinterpret_cast<int4 *>(peer) = *reinterpret_cast<int4 *>(&r);
-                *(reinterpret_cast<int4 *>(peer) + 1) = *(reinterpret_cast<int4 *>(&r) + 1);
+                const uint32_t dst = map_to_rank(smem_u32(&rec[par][rank]), (uint32_t)t);
+                const uint32_t rbar = map_to_rank(my_bar, (uint32_t)t);
+                st_async_v4(dst, cbits, (uint32_t)ci, __float_as_uint(sx[cl]), __float_as_uint(sy[cl]), rbar);
+                st_async_v4(dst + 16, __float_as_uint(sz[cl]), 0u, 0u, 0u, rbar);
             }
-            cluster.sync();
+            mbar_wait_cluster(my_bar, (uint32_t)((it >> 1) & 1));
             unsigned int bb = 0u;
             int bi = INT_MAX;
             for (int r = 0; r < C; ++r) {
-                const unsigned int vb = rec[it & 1][r].bits;
-                const int vi = rec[it & 1][r].idx;
-                if (vb > bb || (vb == bb && vi < bi)) { bb = vb; bi = vi; cx = rec[it & 1][r].x; cy = rec[it & 1][r].y; cz = rec[it & 1][r].z; }
+                const unsigned int vb = rec[par][r].bits;
+                const int vi = rec[par][r].idx;
+                if (vb > bb || (vb == bb && vi < bi)) { bb = vb; bi = vi; cx = rec[par][r].x; cy = rec[par][r].y; cz = rec[par][r].z; }
             }
             far = bi;
         }

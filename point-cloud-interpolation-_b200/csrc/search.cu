@@ -270,21 +270,33 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
 #pragma unroll
             for (int j = 0; j < Q; ++j) { mask[j][0] = 0u; mask[j][1] = 0u; }
             const float4 *cp = tp + c * CHUNK;
+            // register double buffer: the 8 records of the NEXT chunk are requested first, then a warp-level
+            // memory barrier pins those loads above the ~45 math instructions of the CURRENT chunk, so the
+            // shared-memory latency is covered (without it ptxas sinks every LDS next to its first use).
+            float4 R[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) R[p] = cp[p];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
                 uint32_t bit = 1u;
-#pragma unroll 2
-                for (int cc = 0; cc < n_here; ++cc, bit <<= 1, cp += CHUNK) {
+                for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
+                    cp += CHUNK;   // one chunk past the tile end is still inside the ring / barrier block: harmless
+                    float4 Nx[8];
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) Nx[p] = cp[p];
+                    __syncwarp();
                     float4 A[4], Bv[4];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) { A[p] = cp[2 * p]; Bv[p] = cp[2 * p + 1]; }
+                    for (int p = 0; p < 4; ++p) { A[p] = R[2 * p]; Bv[p] = R[2 * p + 1]; }
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
                         const float m = chunk_min<FORM>(A, Bv, qc[j]);
                         const bool hit = MODE == MODE_TOPK ? (m < tau[j]) : (m <= tau[j]);
                         if (hit) mask[j][half] |= bit;
                     }
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) R[p] = Nx[p];
                 }
             }
 
@@ -507,8 +519,8 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
             if (w < 1) w = 1;
             if (w > wmax) w = wmax;
             if (force_w) w = force_w > wmax ? wmax : force_w;
-            // register file: 64K registers per SM, ~88 (Q=2) / ~64 (Q=1) per thread
-            if ((long)w * 32 * c * (q == 2 ? 88 : 64) > 65536) continue;
+            // register file: 64K registers per SM, ~120 (Q=2) / ~96 (Q=1) per thread
+            if ((long)w * 32 * c * (q == 2 ? 128 : 96) > 65536) continue;
             const long items = (long)B * (((long)S + 32L * q * w - 1) / (32L * q * w));
             // too few CTAs for the machine: split the ref range (partial lists are merged afterwards)
             int split = 1;
