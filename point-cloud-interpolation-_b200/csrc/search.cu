@@ -116,11 +116,31 @@ __device__ __forceinline__ f32x2 pair_dist(const float4 &A, const float4 &Bv, co
     }
 }
 
+// Hot-loop variant.  At the kNN call site (form 0) the query norm is the LAST addend and is constant
+// per query, so the prefilter ranks on t = fl(dot' + |r|^2) and skips that add; the threshold it is
+// compared with is moved into t-space conservatively (prefilter_threshold), and the drain re-tests the
+// exact distance, so results are unchanged -- the hot loop just does 4 packed instructions instead of 5.
+template <int FORM>
+__device__ __forceinline__ f32x2 pair_prefilter(const float4 &A, const float4 &Bv, const QueryConst &q) {
+    if (FORM != B200PC_FORM_REF_NORM_FIRST) return pair_dist<FORM>(A, Bv, q);
+    f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w), Z = pack2(Bv.x, Bv.y), W = pack2(Bv.z, Bv.w);
+    f32x2 t = mul2(X, q.a0);
+    t = fma2(Y, q.a1, t);
+    t = fma2(Z, q.a2, t);
+    return add2(t, W);
+}
+// every t with fl(t + nq) < tau satisfies t < (tau - nq) + (2|tau| + |nq|) * 2^-24; one more bit of margin
+template <int FORM>
+__device__ __forceinline__ float prefilter_threshold(float tau, float nq) {
+    if (FORM != B200PC_FORM_REF_NORM_FIRST) return tau;
+    return (tau - nq) + (2.0f * fabsf(tau) + fabsf(nq)) * 1.1920929e-7f;
+}
+
 template <int FORM>
 __device__ __forceinline__ float chunk_min(const float4 (&A)[4], const float4 (&Bv)[4], const QueryConst &q) {
     float d[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) unpack2(pair_dist<FORM>(A[p], Bv[p], q), d[2 * p], d[2 * p + 1]);
+    for (int p = 0; p < 4; ++p) unpack2(pair_prefilter<FORM>(A[p], Bv[p], q), d[2 * p], d[2 * p + 1]);
     float m0 = min3(d[0], d[1], d[2]);
     float m1 = min3(d[3], d[4], d[5]);
     float m2 = min3(d[6], d[7], m0);
@@ -135,6 +155,7 @@ struct SearchArgs {
     const float *qry;      // [B][S][3]
     int N, n_pad, S, k;
     float r2;              // ball radius^2 (fp32)
+    int debug_nodrain;     // measurement only: start with tau = -inf so nothing ever hits
     int n_split, tiles_per_split;
     int64_t *idx_out;      // [B][S][k]   (n_split == 1)
     float *dist_out;       // [B][S][k] or null
@@ -154,24 +175,36 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 }
 constexpr unsigned long long HEAP_SENTINEL = 0xFF800000FFFFFFFFull;  // (+inf, max index)
 
-// max-heap of `n` 64-bit keys, element e of this query at heap[e * stride]; put `nk` at the root
-// and sift it down.  Depth is ceil(log2 n): every lane of a warp runs the same short loop.
-__device__ __forceinline__ void heap_sift_root(unsigned long long *heap, int stride, int n, unsigned long long nk) {
-    int pos = 0;
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+
+// max-heap of 64-bit keys in shared memory: element e of this query lives at byte address hb + e*SB.
+// Put `nk` at the root of a heap holding nB/SB elements and sift it down (depth ceil(log2 n): every
+// lane of a warp runs the same short loop).  PADDED = the element right after the heap is readable and
+// holds key 0, so the right child needs no bounds check (true while streaming, false during heapsort).
+template <bool PADDED>
+__device__ __forceinline__ void heap_sift_root(uint32_t hb, uint32_t SB, uint32_t nB, unsigned long long nk) {
+    uint32_t pos = 0;
     while (true) {
-        const int l = 2 * pos + 1;
-        if (l >= n) break;
-        int c = l;
-        unsigned long long kc = heap[l * stride];
-        if (l + 1 < n) {
-            const unsigned long long kr = heap[(l + 1) * stride];
-            if (kr > kc) { kc = kr; c = l + 1; }
+        const uint32_t l = 2 * pos + SB;
+        if (l >= nB) break;
+        unsigned long long kc = lds_u64(hb + l);
+        uint32_t c = l;
+        if (PADDED || l + SB < nB) {
+            const unsigned long long kr = lds_u64(hb + l + SB);
+            if (kr > kc) { kc = kr; c = l + SB; }
         }
         if (kc <= nk) break;
-        heap[pos * stride] = kc;
+        sts_u64(hb + pos, kc);
         pos = c;
     }
-    heap[pos * stride] = nk;
+    sts_u64(hb + pos, nk);
 }
 
 constexpr int CAND_CAP = 32;  // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a sub-tile
@@ -202,7 +235,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
     int *issued = reinterpret_cast<int *>(smem + STAGES * TILE_BYTES + 8 * 2 * STAGES);   // tiles issued so far
     // top-k: heap [k][QPB] u64, then candidate buffer [CAND_CAP][QPB] u16.   ball: list [k][QPB] u32
     unsigned long long *heap_all = reinterpret_cast<unsigned long long *>(smem + STAGES * TILE_BYTES + BAR_BYTES);
-    unsigned short *cand_all = reinterpret_cast<unsigned short *>(heap_all + (size_t)P.k * QPB);
+    unsigned short *cand_all = reinterpret_cast<unsigned short *>(heap_all + (size_t)(P.k + 1) * QPB);
     int *list_all = reinterpret_cast<int *>(heap_all);
 
     const int lane = threadIdx.x & 31;
@@ -244,8 +277,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
         qc[j] = make_query<FORM>(x, y, z);
         cnt[j] = 0;
         if (MODE == MODE_TOPK) {
-            tau[j] = CUDART_INF_F;
+            tau[j] = P.debug_nodrain ? -CUDART_INF_F : CUDART_INF_F;
             for (int e = 0; e < k; ++e) heap_all[e * QPB + j * NCT + ct] = HEAP_SENTINEL;
+            heap_all[k * QPB + j * NCT + ct] = 0ull;   // pad: the smallest key, never selected as a child
         } else {
             tau[j] = P.r2;
         }
@@ -266,6 +300,13 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
             if (nch > CHUNKS_PER_TILE - c) nch = CHUNKS_PER_TILE - c;
 
             // ---- hot loop: distance + half a min per pair, one compare per chunk, no branches ----
+            float thr[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                float lo, hi;
+                unpack2(qc[j].a3, lo, hi);
+                thr[j] = prefilter_threshold<FORM>(tau[j], lo);
+            }
             uint32_t mask[Q][2];
 #pragma unroll
             for (int j = 0; j < Q; ++j) { mask[j][0] = 0u; mask[j][1] = 0u; }
@@ -292,7 +333,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
                         const float m = chunk_min<FORM>(A, Bv, qc[j]);
-                        const bool hit = MODE == MODE_TOPK ? (m < tau[j]) : (m <= tau[j]);
+                        const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
                         if (hit) mask[j][half] |= bit;
                     }
 #pragma unroll
@@ -306,7 +347,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                 uint32_t m0 = mask[j][0], m1 = mask[j][1];
                 const int slot = j * NCT + ct;
                 if (MODE == MODE_TOPK) {
-                    unsigned long long *heap = heap_all + slot;
+                    const uint32_t hb = smem_u32(heap_all + slot), SB = (uint32_t)QPB * 8u;
                     unsigned short *cand = cand_all + slot;
                     while (__any_sync(FULL, (m0 | m1) != 0u)) {
                         // phase 1: every lane revisits its r-th hit chunk; the chunk's candidates (d < stale tau)
@@ -343,8 +384,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                                 cur &= cur - 1;
                                 const float d = tile_dist<FORM>(tp, off, qc[j]);
                                 if (d < tau[j]) {
-                                    heap_sift_root(heap, QPB, k, ((unsigned long long)order_key(d) << 32) | (uint32_t)(tile_ref0 + off));
-                                    tau[j] = key_to_float((uint32_t)(heap[0] >> 32));
+                                    heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | (uint32_t)(tile_ref0 + off));
+                                    tau[j] = key_to_float((uint32_t)(lds_u64(hb) >> 32));
                                 }
                             }
                         }
@@ -394,12 +435,12 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
         const int slot = j * NCT + ct;
         if (MODE == MODE_TOPK) {
             // in-place heapsort: ascending (distance, index) order
-            unsigned long long *heap = heap_all + slot;
+            const uint32_t hb = smem_u32(heap_all + slot), SB = (uint32_t)QPB * 8u;
             for (int n = k; n > 1; --n) {
-                const unsigned long long top = heap[0];
-                const unsigned long long last = heap[(n - 1) * QPB];
-                heap_sift_root(heap, QPB, n - 1, last);
-                heap[(n - 1) * QPB] = top;
+                const unsigned long long top = lds_u64(hb);
+                const unsigned long long last = lds_u64(hb + (uint32_t)(n - 1) * SB);
+                heap_sift_root<false>(hb, SB, (uint32_t)(n - 1) * SB, last);
+                sts_u64(hb + (uint32_t)(n - 1) * SB, top);
             }
         }
         if (qi >= P.S) continue;
@@ -482,7 +523,7 @@ __global__ void merge_ball_kernel(const int *__restrict__ part_i, const int *__r
 // 5. planning + launch
 // ---------------------------------------------------------------------------------------------
 // per-query shared-memory bytes.  top-k: u64 heap [k] + u16 candidate buffer [CAND_CAP];  ball: u32 list [nsample]
-static size_t query_bytes(int k, int mode) { return mode == MODE_TOPK ? (size_t)k * 8 + (size_t)CAND_CAP * 2 : (size_t)k * 4; }
+static size_t query_bytes(int k, int mode) { return mode == MODE_TOPK ? (size_t)(k + 1) * 8 + (size_t)CAND_CAP * 2 : (size_t)k * 4; }
 static const size_t kMaxSmem = 227 * 1024;
 static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 
@@ -603,6 +644,7 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     SearchArgs a;
     a.packed = packed; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
+    a.debug_nodrain = getenv("B200PC_DEBUG_NODRAIN") != nullptr;
     a.idx_out = idx; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;
