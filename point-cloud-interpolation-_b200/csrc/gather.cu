@@ -2,9 +2,11 @@
 //   index_points        Utils/Pointnet2Utils.py:44-61      (also pytorch3d knn_gather, Utils/Layers.py:396,434)
 //   three_nn weights    Utils/Layers.py:183-186 (variant 0), Utils/Pointnet2Utils.py:301-303 (variant 1)
 //   three_interpolate   Utils/Layers.py:187-188, Utils/Pointnet2Utils.py:304
-// and their gradients.  Rows are moved as 16-byte vectors whenever the channel count and the
-// base addresses allow it; loads of streamed data bypass L1 allocation, index/weight loads are
-// shared by the threads of a row through L1.  Grids are sized in whole waves of 148 SMs.
+// and their gradients.  Rows are moved as 16-byte vectors whenever the channel count and the base
+// addresses allow it, one warp per row with several rows in flight; streamed data bypasses L1
+// allocation.  Grids are capped at 16 CTAs per SM and grid-stride over the rows.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "search.cuh"
 
@@ -24,33 +26,38 @@ static int wave_grid(long work_items, int threads, int per_thread) {
 // ------------------------------------------------------------------------------------------
 // index_points
 // ------------------------------------------------------------------------------------------
-// one thread per 16-byte vector of the output; 4 independent vectors in flight per thread
-template <int UNROLL>
-__global__ void __launch_bounds__(256) gather_vec4_kernel(const float4 *__restrict__ points, const int64_t *__restrict__ idx,
-                                                          int N, int C4, long R, long total, float4 *__restrict__ out,
+// One WARP per output row, ROWS rows in flight per warp: the index of a row is read once (lanes < ROWS,
+// then shuffled), so there is no per-vector division and no redundant index traffic, and every lane has
+// ROWS independent 16-byte loads outstanding before the first store (memory-level parallelism is what
+// bounds a 20-70 us gather).  Lanes stride over the row when C4 > 32.
+template <int ROWS>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4 *__restrict__ points, const int64_t *__restrict__ idx,
+                                                          int N, int C4, long R, long rows_total, float4 *__restrict__ out,
                                                           int *__restrict__ oob) {
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * UNROLL) {
-        float4 val[UNROLL];
-        bool live[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const long v = v0 + u * stride;
-            live[u] = v < total;
-            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live[u]) {
-                const long row = v / C4;
-                const int col = (int)(v - row * C4);
-                const long b = row / R;
-                long i = idx[row];
-                if (i < 0) i += N;
-                if (i < 0 || i >= N) { if (oob) *oob = 1; }
-                else val[u] = ldg_stream(points + ((b * N + i) * C4 + col));
-            }
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long r0 = warp * ROWS; r0 < rows_total; r0 += nwarps * ROWS) {
+        long src = -1;                                   // lane l < ROWS owns row r0 + l
+        if (lane < ROWS && r0 + lane < rows_total) {
+            const long row = r0 + lane;
+            long i = idx[row];
+            if (i < 0) i += N;
+            if (i < 0 || i >= N) { if (oob) *oob = 1; }
+            else src = ((row / R) * N + i) * C4;
         }
+        long so[ROWS];                                   // every lane takes part in the shuffles
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-            if (live[u]) stg_stream(out + (v0 + u * stride), val[u]);
+        for (int u = 0; u < ROWS; ++u) so[u] = __shfl_sync(0xffffffffu, src, u);
+        for (int col = lane; col < C4; col += 32) {
+            float4 v[ROWS];
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u)
+                v[u] = so[u] >= 0 ? ldg_stream(points + so[u] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u)
+                if (r0 + u < rows_total) stg_stream(out + (r0 + u) * C4 + col, v[u]);
+        }
     }
 }
 
@@ -129,40 +136,59 @@ __device__ __forceinline__ float mix3(float a, float wa, float b, float wb, floa
     return __fadd_rn(__fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb)), __fmul_rn(c, wc));
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(256) interp_vec4_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
-                                                          const float *__restrict__ w, int S, int C4, long N, long total,
+// warp per dense row, ROWS rows in flight: lanes < 3*ROWS read the row's three (index, weight) pairs once
+// and shuffle them; every lane then has 3*ROWS independent 16-byte gathers outstanding.
+template <int ROWS>
+__global__ void __launch_bounds__(256) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                          const float *__restrict__ w, int S, int C4, long N, long rows_total,
                                                           float4 *__restrict__ out) {
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * UNROLL) {
-        float4 f[UNROLL][3];
-        float ww[UNROLL][3];
-        bool live[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const long v = v0 + u * stride;
-            live[u] = v < total;
-            if (live[u]) {
-                const long row = v / C4;
-                const int col = (int)(v - row * C4);
-                const long b = row / N;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const long i = idx[row * 3 + j];
-                    ww[u][j] = w[row * 3 + j];
-                    f[u][j] = __ldg(feat + ((b * S + i) * C4 + col));   // sparse rows are re-read ~3N/S times: keep in L1/L2
-                }
-            }
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    // (index, weight) of the NEXT group of rows are requested before the current group is gathered
+    long i_next = 0;
+    float w_next = 0.f;
+    {
+        const long row = warp * ROWS + lane / 3;
+        if (lane < 3 * ROWS && row < rows_total) { i_next = idx[row * 3 + lane % 3]; w_next = w[row * 3 + lane % 3]; }
+    }
+    for (long r0 = warp * ROWS; r0 < rows_total; r0 += nwarps * ROWS) {
+        long src = 0;
+        const float wt = w_next;
+        const long i_cur = i_next;
+        {
+            const long rn = r0 + nwarps * ROWS + lane / 3;
+            if (lane < 3 * ROWS && rn < rows_total) { i_next = idx[rn * 3 + lane % 3]; w_next = w[rn * 3 + lane % 3]; }
         }
+        if (lane < 3 * ROWS) {                          // lane = 3*u + j  ->  neighbour j of row r0+u
+            const long row = r0 + lane / 3;
+            if (row < rows_total) src = ((row / N) * S + i_cur) * C4;
+        }
+        long so[ROWS][3];                                // every lane takes part in the shuffles
+        float ww[ROWS][3];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            if (!live[u]) continue;
-            float4 o;
-            o.x = mix3(f[u][0].x, ww[u][0], f[u][1].x, ww[u][1], f[u][2].x, ww[u][2]);
-            o.y = mix3(f[u][0].y, ww[u][0], f[u][1].y, ww[u][1], f[u][2].y, ww[u][2]);
-            o.z = mix3(f[u][0].z, ww[u][0], f[u][1].z, ww[u][1], f[u][2].z, ww[u][2]);
-            o.w = mix3(f[u][0].w, ww[u][0], f[u][1].w, ww[u][1], f[u][2].w, ww[u][2]);
-            stg_stream(out + (v0 + u * stride), o);
+        for (int u = 0; u < ROWS; ++u)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                so[u][j] = __shfl_sync(0xffffffffu, src, 3 * u + j);
+                ww[u][j] = __shfl_sync(0xffffffffu, wt, 3 * u + j);
+            }
+        for (int col = lane; col < C4; col += 32) {
+            float4 f[ROWS][3];
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) f[u][j] = __ldg(feat + so[u][j] + col);   // sparse rows are re-read ~3N/S times: keep them cached
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) {
+                if (r0 + u >= rows_total) continue;
+                float4 o;
+                o.x = mix3(f[u][0].x, ww[u][0], f[u][1].x, ww[u][1], f[u][2].x, ww[u][2]);
+                o.y = mix3(f[u][0].y, ww[u][0], f[u][1].y, ww[u][1], f[u][2].y, ww[u][2]);
+                o.z = mix3(f[u][0].z, ww[u][0], f[u][1].z, ww[u][1], f[u][2].z, ww[u][2]);
+                o.w = mix3(f[u][0].w, ww[u][0], f[u][1].w, ww[u][1], f[u][2].w, ww[u][2]);
+                stg_stream(out + (r0 + u) * C4 + col, o);
+            }
         }
     }
 }
@@ -227,9 +253,18 @@ extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int
     if (B == 0 || R == 0) return B200PC_OK;
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
-        const long total = (long)B * R * (C / 4);
-        gather_vec4_kernel<4><<<wave_grid(total, 256, 4), 256, 0, st>>>(
-            reinterpret_cast<const float4 *>(points), idx, N, C / 4, (long)R, total, reinterpret_cast<float4 *>(out), oob_flag);
+        const long rows = (long)B * R;
+        const char *tune = getenv("B200PC_GATHER_ROWS");   // tuning override (not part of the ABI)
+        const int rw = tune ? atoi(tune) : 8;
+        if (rw == 8)
+            gather_rows_kernel<8><<<wave_grid(rows * 32 / 8, 256, 1), 256, 0, st>>>(
+                reinterpret_cast<const float4 *>(points), idx, N, C / 4, (long)R, rows, reinterpret_cast<float4 *>(out), oob_flag);
+        else if (rw == 2)
+            gather_rows_kernel<2><<<wave_grid(rows * 32 / 2, 256, 1), 256, 0, st>>>(
+                reinterpret_cast<const float4 *>(points), idx, N, C / 4, (long)R, rows, reinterpret_cast<float4 *>(out), oob_flag);
+        else
+            gather_rows_kernel<4><<<wave_grid(rows * 32 / 4, 256, 1), 256, 0, st>>>(
+                reinterpret_cast<const float4 *>(points), idx, N, C / 4, (long)R, rows, reinterpret_cast<float4 *>(out), oob_flag);
     } else {
         const long total = (long)B * R * C;
         gather_scalar_kernel<<<wave_grid(total, 256, 1), 256, 0, st>>>(points, idx, N, C, (long)R, total, out, oob_flag);
@@ -279,9 +314,14 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
     if (B == 0 || N == 0) return B200PC_OK;
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(feat) && aligned16(out)) {
-        const long total = (long)B * N * (C / 4);
-        interp_vec4_kernel<2><<<wave_grid(total, 256, 2), 256, 0, st>>>(reinterpret_cast<const float4 *>(feat), idx, weight, S,
-                                                                        C / 4, (long)N, total, reinterpret_cast<float4 *>(out));
+        const long rows = (long)B * N;
+        const char *tune = getenv("B200PC_INTERP_ROWS");   // tuning override (not part of the ABI)
+        const int rw = tune ? atoi(tune) : 4;
+        const float4 *f4 = reinterpret_cast<const float4 *>(feat);
+        float4 *o4 = reinterpret_cast<float4 *>(out);
+        if (rw == 8) interp_rows_kernel<8><<<wave_grid(rows * 32 / 8, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
+        else if (rw == 2) interp_rows_kernel<2><<<wave_grid(rows * 32 / 2, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
+        else interp_rows_kernel<4><<<wave_grid(rows * 32 / 4, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
     } else {
         const long total = (long)B * N * C;
         interp_scalar_kernel<<<wave_grid(total, 256, 1), 256, 0, st>>>(feat, idx, weight, S, C, (long)N, total, out);
