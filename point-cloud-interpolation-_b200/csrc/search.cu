@@ -10,7 +10,8 @@
 // Design (why it looks the way it does is argued in DESIGN.md):
 //   1. pack_refs_kernel turns refs [B,N,3] into 16-byte records grouped in PAIRS:
 //      {x0,x1,y0,y1} {z0,z1,w0,w1} (w = |r|^2 rounded as torch does, or 0 for the direct form),
-//      padded to a whole tile with records whose distance is +inf.
+//      padded to a whole tile with records whose distance is +inf; the 4 pairs of a chunk are
+//      XOR-swizzled by the chunk number so that the drain's per-lane re-reads avoid bank conflicts.
 //   2. search_kernel: one TMA-producer warp streams 8 KB tiles of those records into a 4-stage
 //      shared-memory ring with cp.async.bulk + mbarrier; consumer threads own Q queries each and
 //      evaluate 2 refs per instruction with FFMA2/FMUL2/FADD2 in EXACTLY the reference's rounding
@@ -67,7 +68,12 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
             x[h] = 0.0f; y[h] = 0.0f; z[h] = 0.0f; w[h] = CUDART_INF_F;   // 0 + inf = inf
         }
     }
-    float4 *o = packed + ((size_t)b * (n_pad / 2) + p) * 2;
+    // a chunk = 4 pairs = 128 bytes = all 32 banks.  Pair q of chunk c is stored in pair-slot q ^ (c & 3), so
+    // that lanes re-visiting DIFFERENT chunks in the drain spread over the banks instead of all starting at
+    // bank 0 (measured: 11.4 wavefronts per LDS.128 without the swizzle).  The hot loop takes a min over the
+    // whole chunk, so the order of the pairs inside a chunk does not matter to it.
+    const int chunk = p >> 2, slot = (p & 3) ^ (chunk & 3);
+    float4 *o = packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2;
     o[0] = make_float4(x[0], x[1], y[0], y[1]);
     o[1] = make_float4(z[0], z[1], w[0], w[1]);
 }
@@ -147,6 +153,15 @@ __device__ __forceinline__ float chunk_min(const float4 (&A)[4], const float4 (&
     return fminf(m1, m2);
 }
 
+// min over the 4 refs held in two pair records (half a chunk)
+template <int FORM>
+__device__ __forceinline__ float half_chunk_min(const float4 (&H)[4], const QueryConst &q) {
+    float d0, d1, d2, d3;
+    unpack2(pair_prefilter<FORM>(H[0], H[1], q), d0, d1);
+    unpack2(pair_prefilter<FORM>(H[2], H[3], q), d2, d3);
+    return fminf(min3(d0, d1, d2), d3);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 3. the streaming search kernel
 // ---------------------------------------------------------------------------------------------
@@ -212,7 +227,9 @@ constexpr int CAND_CAP = 32;  // per-query buffer: one u16 entry (chunk << 8 | c
 template <int FORM>
 __device__ __forceinline__ float tile_dist(const float4 *tp, int off, const QueryConst &q) {
     float lo, hi;
-    unpack2(pair_dist<FORM>(tp[off & ~1], tp[(off & ~1) + 1], q), lo, hi);   // same packed arithmetic as the hot loop
+    const int chunk = off >> 3, slot = ((off >> 1) & 3) ^ (chunk & 3);     // un-swizzle: where pair (off>>1) lives
+    const float4 *pp = tp + chunk * 8 + slot * 2;
+    unpack2(pair_dist<FORM>(pp[0], pp[1], q), lo, hi);   // same packed arithmetic as the hot loop
     return (off & 1) ? hi : lo;
 }
 
@@ -311,33 +328,68 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
 #pragma unroll
             for (int j = 0; j < Q; ++j) { mask[j][0] = 0u; mask[j][1] = 0u; }
             const float4 *cp = tp + c * CHUNK;
-            // register double buffer: the 8 records of the NEXT chunk are requested first, then a warp-level
-            // memory barrier pins those loads above the ~45 math instructions of the CURRENT chunk, so the
-            // shared-memory latency is covered (without it ptxas sinks every LDS next to its first use).
-            float4 R[8];
+            // register double buffer: records are requested ahead of their use and a warp-level memory barrier
+            // pins those loads above the math of the current group, so the shared-memory latency is covered
+            // (without it ptxas sinks every LDS next to its first use).  Q=2: a whole chunk (8 records) ahead;
+            // Q=1: half a chunk (4 records) ahead, which keeps the kernel under 72 registers so that twice as
+            // many warps stay resident.
+            if (Q >= 2) {
+                float4 R[8];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) R[p] = cp[p];
+                for (int p = 0; p < 8; ++p) R[p] = cp[p];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
-                uint32_t bit = 1u;
-                for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
-                    cp += CHUNK;   // one chunk past the tile end is still inside the ring / barrier block: harmless
-                    float4 Nx[8];
+                for (int half = 0; half < 2; ++half) {
+                    const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
+                    uint32_t bit = 1u;
+                    for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
+                        cp += CHUNK;   // one chunk past the tile end is still inside the ring / barrier block: harmless
+                        float4 Nx[8];
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) Nx[p] = cp[p];
-                    __syncwarp();
-                    float4 A[4], Bv[4];
+                        for (int p = 0; p < 8; ++p) Nx[p] = cp[p];
+                        __syncwarp();
+                        float4 A[4], Bv[4];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) { A[p] = R[2 * p]; Bv[p] = R[2 * p + 1]; }
+                        for (int p = 0; p < 4; ++p) { A[p] = R[2 * p]; Bv[p] = R[2 * p + 1]; }
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const float m = chunk_min<FORM>(A, Bv, qc[j]);
-                        const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
-                        if (hit) mask[j][half] |= bit;
+                        for (int j = 0; j < Q; ++j) {
+                            const float m = chunk_min<FORM>(A, Bv, qc[j]);
+                            const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
+                            if (hit) mask[j][half] |= bit;
+                        }
+#pragma unroll
+                        for (int p = 0; p < 8; ++p) R[p] = Nx[p];
                     }
+                }
+            } else {
+                float4 H[4];
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) R[p] = Nx[p];
+                for (int p = 0; p < 4; ++p) H[p] = cp[p];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
+                    uint32_t bit = 1u;
+                    for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
+                        float4 N1[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) N1[p] = cp[4 + p];
+                        __syncwarp();
+                        float ma[Q];
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) ma[j] = half_chunk_min<FORM>(H, qc[j]);
+                        cp += CHUNK;
+                        float4 N2[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) N2[p] = cp[p];
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            const float m = fminf(ma[j], half_chunk_min<FORM>(N1, qc[j]));
+                            const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
+                            if (hit) mask[j][half] |= bit;
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) H[p] = N2[p];
+                    }
                 }
             }
 
@@ -359,9 +411,13 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                                 if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
                                 else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
                                 const float4 *dp = tp + (c + cc) * CHUNK;
+                                const int sw = (c + cc) & 3;
                                 float d[8];
 #pragma unroll
-                                for (int p = 0; p < 4; ++p) unpack2(pair_dist<FORM>(dp[2 * p], dp[2 * p + 1], qc[j]), d[2 * p], d[2 * p + 1]);
+                                for (int p = 0; p < 4; ++p) {
+                                    const float4 *pp = dp + 2 * (p ^ sw);
+                                    unpack2(pair_dist<FORM>(pp[0], pp[1], qc[j]), d[2 * p], d[2 * p + 1]);
+                                }
                                 uint32_t cm = 0u;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) cm |= (d[i] < tau[j]) ? (1u << i) : 0u;
@@ -399,9 +455,13 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                             else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
                             const int off0 = (c + cc) * CHUNK;
                             const float4 *dp = tp + off0;
+                            const int sw = (c + cc) & 3;
                             float d[8];
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) unpack2(pair_dist<FORM>(dp[2 * p], dp[2 * p + 1], qc[j]), d[2 * p], d[2 * p + 1]);
+                            for (int p = 0; p < 4; ++p) {
+                                const float4 *pp = dp + 2 * (p ^ sw);
+                                unpack2(pair_dist<FORM>(pp[0], pp[1], qc[j]), d[2 * p], d[2 * p + 1]);
+                            }
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 if (d[i] <= tau[j] && cnt[j] < k) { list[cnt[j] * QPB] = tile_ref0 + off0 + i; ++cnt[j]; }
@@ -560,8 +620,8 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
             if (w < 1) w = 1;
             if (w > wmax) w = wmax;
             if (force_w) w = force_w > wmax ? wmax : force_w;
-            // register file: 64K registers per SM, ~120 (Q=2) / ~96 (Q=1) per thread
-            if ((long)w * 32 * c * (q == 2 ? 128 : 96) > 65536) continue;
+            // register file: 64K registers per SM, ~125 (Q=2) / <=72 (Q=1) per thread
+            if ((long)w * 32 * c * (q == 2 ? 128 : 72) > 65536) continue;
             const long items = (long)B * (((long)S + 32L * q * w - 1) / (32L * q * w));
             // too few CTAs for the machine: split the ref range (partial lists are merged afterwards)
             int split = 1;
