@@ -237,32 +237,40 @@ def pointinet_inputs(pair, n, dev=None, pinned=False):
 
 def pointinet_bench(dev, rank, steps, flush, barrier, dist):
     """BASELINE metric (i): PointINet interpolated frames/s at 16384 points, batch 1, t=0.5, random
-    weights (the reference ships none).  Every rank interpolates its own frame pairs.
-    returns (device-resident seconds/frame, host-buffer seconds/frame) as the max over ranks."""
+    weights (the reference ships none).  Every rank interpolates its own frame pairs.  Three variants,
+    seconds per frame as the max over ranks:
+      eager   - the module called like the reference calls it (one Python dispatch per op), inputs resident
+      graph   - the same forward captured once as a CUDA graph (b200pc.pointinet.GraphedPointINet: RNG tape
+                refilled on the CPU generator each frame, BatchNorm folded), inputs resident
+      graph_e2e - graph variant fed from pinned HOST buffers, fused frame copied back to the host"""
     from b200pc import pointinet
     torch.manual_seed(0)
     net = pointinet.PointINet().eval().to(dev)
     dev_in = pointinet_inputs(100 + rank, NPTS, dev=dev)
     host_in = pointinet_inputs(100 + rank, NPTS, pinned=True)
     host_out = torch.empty(1, 4, NPTS).pin_memory()
+    graphed = pointinet.GraphedPointINet(state_dict=net.state_dict(), batch=1, npoints=NPTS, extra=1, t=0.5, device=dev)
+    graphed.capture(*dev_in[:4])
 
-    def resident():
+    def eager():
         with torch.no_grad():
             net(*dev_in)
 
-    def hosted():
-        with torch.no_grad():
-            host_out.copy_(net(*[x.to(dev, non_blocking=True) for x in host_in]), non_blocking=True)
+    def graph():
+        graphed(*dev_in[:4])
 
-    out = []
-    for fn in (resident, hosted):
+    def graph_e2e():
+        host_out.copy_(graphed(*host_in[:4]), non_blocking=True)
+
+    out = {}
+    for name, fn in (("eager", eager), ("graph", graph), ("graph_e2e", graph_e2e)):
         torch.manual_seed(3000 + rank)
         secs = timed_steps(fn, steps, 3, flush, torch.cuda.synchronize, barrier)
         tm = torch.tensor([secs / steps], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        out.append(float(tm.item()))
-    return out[0], out[1]
+        out[name] = float(tm.item())
+    return out
 
 
 def pointinet_cpu_baseline():
@@ -346,10 +354,10 @@ def main():
     e2e_value = queries_per_step * e2e_steps / float(et.item()) / 1e9
 
     # ---- metric (i): PointINet frames/s, every rank on its own frame pairs ----------------------
-    pn_dev = pn_host = None
+    pn = None
     if args.extras:
         try:
-            pn_dev, pn_host = pointinet_bench(dev, rank, max(3, min(args.steps, 10)), flush, barrier, dist)
+            pn = pointinet_bench(dev, rank, max(3, min(args.steps, 20)), flush, barrier, dist)
         except Exception as e:  # pragma: no cover
             if rank == 0:
                 print("pointinet bench failed: %r" % (e,), file=sys.stderr)
@@ -393,10 +401,12 @@ def main():
             # pack_refs_kernel + search_kernel per knn_point call (no ref split at C2), timed steps only
             "gpu_launches": int(args.steps * 2), "abi_calls_incl_warmup": int(abi_calls),
             "roofline": roofline, "cpu_baseline": cpu_baseline}
-    if pn_dev:
+    if pn:
         line["pointinet"] = {"metric": "pointinet_interp_frames_per_s", "workload": "C1: PointINet forward, 16384 points, batch 1 per GPU, t=0.5, random weights",
-                             "value": world / pn_dev, "e2e_value": world / pn_host, "unit": "frames/s", "ms_per_frame": pn_dev * 1e3,
-                             "ms_per_frame_e2e": pn_host * 1e3, "paper_rtx2060_frames_per_s": 4.9}
+                             "value": world / pn["graph"], "e2e_value": world / pn["graph_e2e"], "eager_value": world / pn["eager"], "unit": "frames/s",
+                             "ms_per_frame": pn["graph"] * 1e3, "ms_per_frame_e2e": pn["graph_e2e"] * 1e3, "ms_per_frame_eager": pn["eager"] * 1e3,
+                             "note": "value/e2e_value: forward captured as one CUDA graph (RNG tape, folded BatchNorm); eager_value: per-op dispatch like the reference",
+                             "paper_rtx2060_frames_per_s": 4.9}
         if world == 1:
             try:
                 csec, cthr = pointinet_cpu_baseline()

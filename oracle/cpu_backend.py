@@ -44,4 +44,5 @@ def make():
         three_nn_weights=_three_nn_weights,
         three_interpolate=_three_interpolate,
         knn_points=_knn_points,
-        knn_gather=lambda x, idx, lengths=None: ref_torch.gather_rows(x, idx))
+        knn_gather=lambda x, idx, lengths=None: ref_torch.gather_rows(x, idx),
+        randperm=lambda n, keep, device: torch.randperm(n)[:keep].to(device))

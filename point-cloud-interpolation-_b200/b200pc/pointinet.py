@@ -20,13 +20,72 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-def cuda_backend():
-    from . import pointnet2_utils as P, pytorch3d_shim as S
-    return types.SimpleNamespace(
-        farthest_point_sample=P.farthest_point_sample, index_points=P.index_points,
-        query_ball_point=P.query_ball_point, knn_point=P.knn_point,
+class RngTape:
+    """The CPU-RNG draws of one forward, in the reference's order: one torch.randint per FPS call
+    (Utils/Pointnet2Utils.py:76) and two torch.randperm per fused frame (PointINet20230424/models/
+    layers.py:402-403).  mode "eager": draw and upload on the spot (what the reference does).
+    mode "record": same, but remember the sequence and keep every draw in a slice of one flat device
+    tensor.  mode "replay": hand out those slices without touching the RNG -- this is what runs inside a
+    CUDA-graph capture; `refill()` then redraws the whole sequence on the CPU generator (same calls, same
+    order, so torch.manual_seed still reproduces the reference) and uploads it with ONE copy per frame."""
+
+    def __init__(self, device):
+        self.device, self.mode = device, "eager"
+        self.specs, self.views, self.pos = [], [], 0
+        self.flat_dev = self.flat_host = None
+
+    def _draw(self, spec):
+        kind, a, b = spec
+        return torch.randint(0, a, (b,), dtype=torch.long) if kind == "randint" else torch.randperm(a)[:b]
+
+    def _next(self, spec):
+        if self.mode == "eager":
+            return self._draw(spec).to(self.device)
+        if self.mode == "record":
+            self.specs.append(spec)
+            v = self._draw(spec).to(self.device)
+            self.views.append(v)
+            return v
+        v = self.views[self.pos]; self.pos += 1           # replay
+        assert self.specs[self.pos - 1] == spec, "RNG tape out of sync with the recorded forward"
+        return v
+
+    def randint(self, high, count):
+        return self._next(("randint", int(high), int(count)))
+
+    def randperm(self, n, keep):
+        return self._next(("randperm", int(n), int(keep)))
+
+    def finish_recording(self):
+        total = sum(s[2] for s in self.specs)
+        self.flat_dev = torch.empty(total, dtype=torch.long, device=self.device)
+        self.flat_host = torch.empty(total, dtype=torch.long).pin_memory()
+        off, views = 0, []
+        for s, old in zip(self.specs, self.views):
+            v = self.flat_dev[off:off + s[2]]; v.copy_(old); views.append(v); off += s[2]
+        self.views, self.mode = views, "replay"
+
+    def refill(self):
+        off = 0
+        for s in self.specs:
+            self.flat_host[off:off + s[2]] = self._draw(s); off += s[2]
+        self.flat_dev.copy_(self.flat_host, non_blocking=True)
+        self.pos = 0
+
+
+def cuda_backend(tape=None):
+    from . import ops, pointnet2_utils as P, pytorch3d_shim as S
+    be = types.SimpleNamespace(
+        index_points=P.index_points, query_ball_point=P.query_ball_point, knn_point=P.knn_point,
         three_nn_weights=P.three_nn_weights, three_interpolate=P.three_interpolate,
-        knn_points=S.knn_points, knn_gather=S.knn_gather)
+        knn_points=S.knn_points, knn_gather=S.knn_gather, tape=tape)
+    if tape is None:
+        be.farthest_point_sample = P.farthest_point_sample
+        be.randperm = lambda n, keep, device: torch.randperm(n)[:keep].to(device)
+    else:
+        be.farthest_point_sample = lambda xyz, npoint: ops.fps(xyz, npoint, tape.randint(xyz.shape[1], xyz.shape[0]))
+        be.randperm = lambda n, keep, device: tape.randperm(n, keep)
+    return be
 
 
 def _pointwise_mlp(channels):
@@ -153,15 +212,17 @@ class PointsFusion(nn.Module):
         cf = lambda x: x.permute(0, 3, 1, 2).contiguous()
         return cf(feat), cf(res.knn), cf(extra)
 
-    def forward(self, xyz1, xyz2, feats1, feats2, k, t):
+    def forward(self, xyz1, xyz2, feats1, feats2, k, t, t_host=None):
         B, _, N = xyz1.shape
-        t_host = t.detach().reshape(B).to("cpu", torch.float32)
+        if t_host is None:
+            t_host = t.detach().reshape(B).to("cpu", torch.float32)        # device->host sync, as in the reference
+        rp = getattr(self.be, "randperm", None) or (lambda n, keep, device: torch.randperm(n)[:keep].to(device))
         fa, ga, ea = [], [], []
         for i in range(B):
             n2 = int(N * t_host[i]); n1 = N - n2
             k2 = int(k * t_host[i]); k1 = k - k2
-            sel1 = torch.randperm(N)[:n1].to(xyz1.device)                 # CPU generator, like the reference
-            sel2 = torch.randperm(N)[:n2].to(xyz1.device)
+            sel1 = rp(N, n1, xyz1.device)                                  # CPU generator, like the reference
+            sel2 = rp(N, n2, xyz1.device)
             a, b = xyz1[i:i + 1], xyz2[i:i + 1]
             mixed = torch.cat((a[:, :, sel1], b[:, :, sel2]), dim=-1)
             f1, g1, e1 = self._neighbours(mixed, a, feats1[i:i + 1], k1)
@@ -182,13 +243,98 @@ class PointINet(nn.Module):
                 p.requires_grad = False
         self.fusion = PointsFusion(be, 4, [64, 64, 128])
 
-    def forward(self, points1, points2, features1, features2, t):
+    def forward(self, points1, points2, features1, features2, t, t_host=None):
         """points [B,3+C,N] (xyz + extra channels), features [B,3,N] (zeros for LiDAR), t [B] in (0,1)
-        -> fused frame [B,3+C,N] at time t."""
+        -> fused frame [B,3+C,N] at time t.  t_host: the same values on the CPU (avoids the device->host
+        read of t; required under CUDA-graph capture)."""
         extra1, extra2 = points1[:, 3:].contiguous(), points2[:, 3:].contiguous()
         xyz1, xyz2 = points1[:, :3].contiguous(), points2[:, :3].contiguous()
         with torch.no_grad():
             fwd = self.flow(xyz1, xyz2, features1, features2)
             bwd = self.flow(xyz2, xyz1, features2, features1)
         tt = t.view(-1, 1, 1)
-        return self.fusion(xyz1 + fwd * tt, xyz2 + bwd * (1 - tt), extra1, extra2, 32, tt)
+        return self.fusion(xyz1 + fwd * tt, xyz2 + bwd * (1 - tt), extra1, extra2, 32, tt, t_host)
+
+    def fold_batchnorm_(self):
+        """inference only: fold every eval-mode BatchNorm into the 1x1 convolution in front of it
+        (71 fewer launches per frame).  Changes results at the 1e-6 level."""
+        assert not self.training, "fold_batchnorm_ is for eval mode"
+        for m in list(self.modules()):
+            if isinstance(m, nn.Sequential):
+                _fold_sequential_(m)
+        return self
+
+
+def _fold_sequential_(seq):
+    mods = list(seq.children())
+    out, i = [], 0
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if isinstance(m, (nn.Conv1d, nn.Conv2d)) and isinstance(nxt, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            scale = nxt.weight / torch.sqrt(nxt.running_var + nxt.eps)
+            with torch.no_grad():
+                m.weight.mul_(scale.view(-1, *([1] * (m.weight.dim() - 1))))
+                m.bias.copy_((m.bias - nxt.running_mean) * scale + nxt.bias)
+            out.append(m); i += 2
+        else:
+            out.append(m); i += 1
+    for k in list(seq._modules.keys()):
+        del seq._modules[k]
+    for j, m in enumerate(out):
+        seq.add_module(str(j), m)
+
+
+class GraphedPointINet:
+    """PointINet forward captured ONCE as a CUDA graph for a fixed (batch, points, t): per frame the host
+    only redraws the RNG tape, copies the inputs into the static buffers and replays the graph -- the
+    ~650 kernel launches and their Python dispatch disappear from the frame time."""
+
+    def __init__(self, state_dict=None, batch=1, npoints=16384, extra=1, t=0.5, device="cuda", fold_bn=True, freeze=1):
+        self.device = torch.device(device)
+        self.tape = RngTape(self.device)
+        self.net = PointINet(freeze=freeze, backend=cuda_backend(self.tape)).eval()
+        if state_dict is not None:
+            self.net.load_state_dict(state_dict)
+        self.net.to(self.device)
+        if fold_bn:
+            self.net.fold_batchnorm_()
+        self.t_host = torch.full((batch,), float(t), dtype=torch.float32)
+        self.static_in = [torch.zeros(batch, 3 + extra, npoints, device=self.device), torch.zeros(batch, 3 + extra, npoints, device=self.device),
+                          torch.zeros(batch, 3, npoints, device=self.device), torch.zeros(batch, 3, npoints, device=self.device),
+                          self.t_host.to(self.device)]
+        self.graph = None
+        self.static_out = None
+
+    def _forward(self):
+        with torch.no_grad():
+            return self.net(*self.static_in, t_host=self.t_host)
+
+    def capture(self, points1, points2, features1, features2):
+        for dst, src in zip(self.static_in[:4], (points1, points2, features1, features2)):
+            dst.copy_(src)
+        self.tape.mode = "record"
+        self._forward()                                   # eager warm-up: records the RNG sequence, sizes every workspace
+        self.tape.finish_recording()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.tape.pos = 0
+            self._forward()                               # warm-up on the capture stream
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        self.tape.pos = 0
+        with torch.cuda.graph(self.graph):
+            self.static_out = self._forward()
+        return self
+
+    def __call__(self, points1, points2, features1, features2):
+        """inputs: CUDA or pinned-host tensors of the captured shapes -> fused frame (static output tensor)."""
+        if self.graph is None:
+            self.capture(points1, points2, features1, features2)
+        self.tape.refill()
+        for dst, src in zip(self.static_in[:4], (points1, points2, features1, features2)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

@@ -59,3 +59,26 @@ def test_flownet3d_gpu_matches_cpu_port(cuda_dev):
     with torch.no_grad():
         got = gpu_net(p1.to(cuda_dev), p2.to(cuda_dev), f1.to(cuda_dev), f2.to(cuda_dev)).cpu()
     torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4)
+
+
+def test_graphed_pointinet_matches_eager(cuda_dev):
+    """CUDA-graph replay with the RNG tape == eager forward under the same torch.manual_seed (no BN folding),
+    and with BN folded within 1e-4."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    eager = pointinet.PointINet().eval().to(cuda_dev)
+    sd = eager.state_dict()
+    ins = [x.to(cuda_dev) for x in _inputs(4096)]
+    t = torch.tensor([0.5], device=cuda_dev)
+    for fold, tol in ((False, 1e-6), (True, 2e-4)):
+        g = pointinet.GraphedPointINet(state_dict=sd, batch=1, npoints=4096, extra=1, t=0.5, device=cuda_dev, fold_bn=fold)
+        g.capture(*ins)
+        for seed in (11, 12):
+            torch.manual_seed(seed)
+            with torch.no_grad():
+                want = eager(*ins, t)
+            torch.manual_seed(seed)
+            got = g(*ins).clone()
+            err = (got - want).abs().amax(dim=1).reshape(-1)
+            assert (err < max(tol, 1e-6) * 50).float().mean() > 0.995, (fold, seed, float(err.max()))
