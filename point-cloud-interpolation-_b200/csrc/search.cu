@@ -28,6 +28,7 @@
 //      a small merge kernel combines the partial lists.
 #include "search.cuh"
 
+#include <math.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -605,6 +606,7 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
 
     double best_score = -1.0;
     int best_q = 1, best_w = 1, best_split = 1;
+    const double lnk = 1.0 + log(fmax(1.0, (double)N / k));
     for (int q = 2; q >= 1; --q) {
         if (force_q && q != force_q) continue;
         for (int c = 1; c <= 8; ++c) {                       // target CTAs per SM
@@ -613,36 +615,33 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
             int wmax = (int)((budget - kFixedSmem) / (32 * q * qb));
             if (wmax > MAX_WARPS) wmax = MAX_WARPS;
             const long slots = (long)sms * c;
-            // queries per CTA if the S queries of each batch item are spread over the slots
-            long ipb = slots / B;                            // items (CTAs) per batch item, one wave
-            if (ipb < 1) ipb = 1;
-            int w = (int)((((long)S + ipb - 1) / ipb + 32 * q - 1) / (32 * q));
-            if (w < 1) w = 1;
-            if (w > wmax) w = wmax;
-            if (force_w) w = force_w > wmax ? wmax : force_w;
-            // register file: 64K registers per SM, ~125 (Q=2) / <=72 (Q=1) per thread
-            if ((long)w * 32 * c * (q == 2 ? 128 : 72) > 65536) continue;
-            const long items = (long)B * (((long)S + 32L * q * w - 1) / (32L * q * w));
-            // too few CTAs for the machine: split the ref range (partial lists are merged afterwards)
-            int split = 1;
-            if (items * 2 <= slots) {
-                split = (int)(slots / items);
-                if (split > MAX_SPLIT) split = MAX_SPLIT;
-                if (split > pl->n_tiles) split = pl->n_tiles;
-                if (split < 1) split = 1;
+            for (int split = 1; split <= MAX_SPLIT && split <= pl->n_tiles; split = split < 4 ? split + 1 : split * 2) {
+                if (force_split && split != (force_split > pl->n_tiles ? pl->n_tiles : force_split)) continue;
+                // queries per CTA if the work items (query block x ref split) of each batch item fill the slots
+                long ipb = slots / ((long)B * split);           // query blocks per batch item, one wave
+                if (ipb < 1) ipb = 1;
+                int w = (int)((((long)S + ipb - 1) / ipb + 32 * q - 1) / (32 * q));
+                if (w < 1) w = 1;
+                if (w > wmax) w = wmax;
+                if (force_w) w = force_w > wmax ? wmax : force_w;
+                // register file: 64K registers per SM, ~125 (Q=2) / <=72 (Q=1) per thread
+                if ((long)w * 32 * c * (q == 2 ? 128 : 72) > 65536) continue;
+                const long items = (long)B * (((long)S + 32L * q * w - 1) / (32L * q * w));
+                const int tps = (pl->n_tiles + split - 1) / split;
+                const int real_split = (pl->n_tiles + tps - 1) / tps;
+                const long ctas = items * real_split;
+                const long waves = (ctas + slots - 1) / slots;
+                const double wave_eff = (double)ctas / (double)(waves * slots);
+                const double pad_eff = (double)B * S / ((double)items * 32 * q * w);
+                // resident warps per SM: below ~16 the SM cannot hide the drain's latency (and below 4 it idles)
+                const double resident = fmin((double)c, (double)ctas / sms) * w;
+                const double occ = pow(fmin(1.0, resident / 16.0), 0.8);
+                // a split repeats the warm-up of the k-best list in every ref range: ~k(1+ln(n/k)) candidates each
+                const double drain = real_split * (1.0 + log(fmax(1.0, (double)N / real_split / k))) / lnk;
+                const double work = 0.5 + 0.5 * drain + (real_split > 1 ? 0.05 : 0.0);
+                const double score = wave_eff * pad_eff * occ / work + 1e-3 * (q == 2) + 1e-5 * resident;
+                if (score > best_score) { best_score = score; best_q = q; best_w = w; best_split = real_split; }
             }
-            if (force_split) split = force_split > pl->n_tiles ? pl->n_tiles : (force_split > MAX_SPLIT ? MAX_SPLIT : force_split);
-            const int tps = (pl->n_tiles + split - 1) / split;
-            split = (pl->n_tiles + tps - 1) / tps;
-            const long ctas = items * split;
-            const long waves = (ctas + slots - 1) / slots;
-            const double wave_eff = (double)ctas / (double)(waves * slots);
-            const double pad_eff = (double)B * S / ((double)items * 32 * q * w);
-            const double warps = (double)c * w;
-            const double occ = warps >= 12 ? 1.0 : 0.55 + 0.45 * warps / 12.0;   // few resident warps hide latency badly
-            const double split_cost = split > 1 ? 0.9 : 1.0;
-            const double score = wave_eff * pad_eff * occ * split_cost + 1e-3 * (q == 2) + 1e-4 * warps;
-            if (score > best_score) { best_score = score; best_q = q; best_w = w; best_split = split; }
         }
     }
     pl->q_per_thread = best_q;
@@ -683,6 +682,10 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && k >= 1, "search: bad sizes B=%d N=%d S=%d k=%d", B, N, S, k);
     B200PC_REQUIRE(idx || dist, "search: no output requested");
     if (B == 0 || S == 0) return B200PC_OK;
+    {   // small reference sets: warp-per-query kernel, one launch, no workspace (small_search.cu)
+        const int rc_small = run_small(ref, qry, B, N, S, k, form, mode, r2, idx, dist, st);
+        if (rc_small != -100) return rc_small;
+    }
     SearchPlan pl;
     if (!plan_search(B, N, S, k, mode, &pl)) {
         set_error("search: list length k=%d does not fit in shared memory", k);

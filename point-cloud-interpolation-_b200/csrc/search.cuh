@@ -33,4 +33,8 @@ int run_topk(const float *ref, const float *qry, int B, int N, int S, int k, int
 int run_ball(const float *ref, const float *qry, int B, int N, int S, float r2, int nsample, int64_t *idx,
              void *ws, size_t ws_bytes, cudaStream_t st);
 
+// warp-per-query path for N <= 1024 (small_search.cu); returns -100 when it declines the problem
+int run_small(const float *ref, const float *qry, int B, int N, int S, int k, int form, int mode, float r2, int64_t *idx,
+              float *dist, cudaStream_t st);
+
 }  // namespace b200pc

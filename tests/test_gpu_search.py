@@ -29,12 +29,20 @@ CASES = [
     (3, 513, 31, 3),        # one ref past a tile boundary
     (1, 5, 9, 5),           # k == N
     (1, 2048, 100, 32),
+    (2, 1024, 256, 8),      # SetUpConv 1024 x 256 (refs = 256 in the model; both orientations are small-path shapes)
+    (1, 700, 5000, 16),     # small refs, many queries: the planner keeps the streaming kernel
+    (1, 1024, 64, 100),     # large k on the warp-per-query path
 ]
 
 
+@pytest.mark.parametrize("small_path", ["1", "0"])     # N <= 1024: warp-per-query kernel vs the streaming kernel
 @pytest.mark.parametrize("B,N,S,k", CASES)
 @pytest.mark.parametrize("form", [0, 1, 2])
-def test_knn_matches_strict_oracle(cuda_dev, B, N, S, k, form):
+def test_knn_matches_strict_oracle(cuda_dev, monkeypatch, B, N, S, k, form, small_path):
+    if small_path == "0":
+        if N > 1024:
+            pytest.skip("streaming kernel is the only path for N > 1024")
+        monkeypatch.setenv("B200PC_SMALL_PATH", "0")
     a, b = synth.batch_pairs(10, B, max(N, S))
     ref, qry = a[:, :N].copy(), b[:, :S].copy()
     idx, dist = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), k, form, want_dist=True)
@@ -101,8 +109,13 @@ BALL_CASES = [
 ]
 
 
+@pytest.mark.parametrize("small_path", ["1", "0"])
 @pytest.mark.parametrize("B,N,S,radius,nsample", BALL_CASES)
-def test_ball_query_matches_strict_oracle(cuda_dev, B, N, S, radius, nsample):
+def test_ball_query_matches_strict_oracle(cuda_dev, monkeypatch, B, N, S, radius, nsample, small_path):
+    if small_path == "0":
+        if N > 1024:
+            pytest.skip("streaming kernel is the only path for N > 1024")
+        monkeypatch.setenv("B200PC_SMALL_PATH", "0")
     a, b = synth.batch_pairs(20, B, max(N, S))
     xyz, new_xyz = a[:, :N].copy(), b[:, :S].copy()
     out = P.query_ball_point(radius, nsample, _t(xyz, cuda_dev), _t(new_xyz, cuda_dev))
