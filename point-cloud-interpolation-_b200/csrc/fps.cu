@@ -17,6 +17,7 @@
 // barrier latency of a round, reported by bench.py as microseconds per round.
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -72,7 +73,16 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
     float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
     if (C > 1) cluster.sync(); else __syncthreads();
 
+#ifdef B200PC_FPS_TIMING
+    long long acc[5] = {0, 0, 0, 0, 0}, t0 = 0;
+#define TICK(i) { const long long now = clock64(); acc[i] += now - t0; t0 = now; }
+#else
+#define TICK(i)
+#endif
     for (int it = 0; it < npoint; ++it) {
+#ifdef B200PC_FPS_TIMING
+        t0 = clock64();
+#endif
         if (rank == 0 && t == 0) out[(size_t)b * npoint + it] = far;
         if (it == npoint - 1) break;  // the last pick needs no further update
 
@@ -99,6 +109,7 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
             lmax = mind[0];
         }
 
+        TICK(0)
         // ---- block arg-max (first index) with ONE barrier: the pair (max bits, ~index) is reduced as a
         // 64-bit key -- two REDUX per warp, one shared write per warp, one __syncthreads, two REDUX again.
         int lp = 0;
@@ -109,13 +120,16 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
         const unsigned int linv = 0xffffffffu - (unsigned int)(cta_base + lp * FPS_T + t);   // larger = lower index
         unsigned int wbits = __reduce_max_sync(0xffffffffu, lbits);
         unsigned int winv = __reduce_max_sync(0xffffffffu, lbits == wbits ? linv : 0u);
+        TICK(1)
         if (lane == 0) warp_key[it & 1][warp] = make_uint2(wbits, winv);
         __syncthreads();
+        TICK(2)
         const uint2 wk = warp_key[it & 1][lane & (FPS_WARPS - 1)];
         const unsigned int cbits = __reduce_max_sync(0xffffffffu, wk.x);
         const unsigned int cinv = __reduce_max_sync(0xffffffffu, wk.x == cbits ? wk.y : 0u);
         const int ci = (int)(0xffffffffu - cinv);
         const int cl = ci - cta_base;
+        TICK(3)
 
         if (C == 1) {
             far = ci;
@@ -134,16 +148,27 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
                 st_async_v4(dst + 16, __float_as_uint(sz[cl]), 0u, 0u, 0u, rbar);
             }
             mbar_wait_cluster(my_bar, (uint32_t)((it >> 1) & 1));
-            unsigned int bb = 0u;
-            int bi = INT_MAX;
-            for (int r = 0; r < C; ++r) {
-                const unsigned int vb = rec[par][r].bits;
-                const int vi = rec[par][r].idx;
-                if (vb > bb || (vb == bb && vi < bi)) { bb = vb; bi = vi; cx = rec[par][r].x; cy = rec[par][r].y; cz = rec[par][r].z; }
-            }
+            // every warp picks the winner among the C records in parallel: lane r holds record r,
+            // two REDUX give (max bits, lowest index), one ballot finds the lane that owns it
+            const FpsRecord mine = rec[par][lane < C ? lane : 0];
+            const unsigned int vb = lane < C ? mine.bits : 0u;
+            const unsigned int bb = __reduce_max_sync(0xffffffffu, vb);
+            const unsigned int vinv = (lane < C && vb == bb) ? 0xffffffffu - (unsigned int)mine.idx : 0u;
+            const unsigned int binv = __reduce_max_sync(0xffffffffu, vinv);
+            const int src = __ffs(__ballot_sync(0xffffffffu, lane < C && vb == bb && vinv == binv)) - 1;
+            const int bi = (int)(0xffffffffu - binv);
+            cx = __shfl_sync(0xffffffffu, mine.x, src);
+            cy = __shfl_sync(0xffffffffu, mine.y, src);
+            cz = __shfl_sync(0xffffffffu, mine.z, src);
             far = bi;
         }
+        TICK(4)
     }
+#ifdef B200PC_FPS_TIMING
+    if (rank == 0 && t == 0 && b == 0)
+        printf("fps timing (cycles/round, C=%d P=%d): update %lld | warp redux %lld | sts+bar %lld | block redux %lld | exchange %lld\n", C, P,
+               acc[0] / npoint, acc[1] / npoint, acc[2] / npoint, acc[3] / npoint, acc[4] / npoint);
+#endif
     if (C > 1) cluster.sync();  // nobody exits while a peer may still write into its shared memory
 }
 
@@ -170,9 +195,18 @@ static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t 
 // cluster size and points-per-thread for a cloud of N points in a batch of B
 static void fps_shape(int B, int N, int *C_out, int *P_out) {
     const int sms = sm_count();
+    // Measured (tools/fps_timing_probe.py, tools/fps_time.py): a single CTA needs ~560 cycles per round plus ~12 per
+    // point held by a thread; a cluster adds ~600-750 cycles of DSMEM exchange.  So one CTA whenever the cloud fits
+    // its registers (8192 points); otherwise spread to ~4 points per thread while the grid stays within half of the
+    // SMs (16384 points: 0.61 us/round at C=8 for B<=8, 0.70 at C=4 for B=16, against 0.88 at C=2).
     int C = 1;
-    while (C < FPS_MAX_CLUSTER && (long)C * FPS_T * 16 < N) C *= 2;          // capacity
-    while (C < 8 && (long)B * C * 2 <= sms && (long)C * FPS_T * 2 <= N) C *= 2;   // latency: spread while SMs are idle
+    while (C < FPS_MAX_CLUSTER && (long)C * FPS_T * 16 < N) C *= 2;
+    if (C > 1)
+        while (C < 8 && (long)B * C * 4 <= sms && (long)C * FPS_T * 4 < N) C *= 2;
+    if (const char *e = getenv("B200PC_FPS_CLUSTER")) {   // tuning override (not part of the ABI)
+        const int f = atoi(e);
+        if (f >= 1 && f <= FPS_MAX_CLUSTER && (long)f * FPS_T * 16 >= N) C = f;
+    }
     int P = 1;
     while ((long)C * FPS_T * P < N) P *= 2;
     *C_out = C; *P_out = P;
