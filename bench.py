@@ -377,13 +377,16 @@ def main():
         fma_tf, fma_ms = None, None
     peak = fma_tf if fma_tf else FP32_NOMINAL_TFLOPS
     roofline = {"bound": "fp32_cuda_core", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, one `ncu --set full` capture of this
+                # workload (profiles/r01_ncu_knn.txt): the packed refs are read once, results stay in L2
+                "traffic": 3706112,
                 "peak_source": "b200pc_fma_peak FFMA2 micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)"
                 if fma_tf else "nominal",
                 "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": achieved / FP32_NOMINAL_TFLOPS,
                 "algorithmic": "8 FLOP per (query, ref) pair x %d pairs per launch" % pairs,
                 "note": "K=3 contraction on FP32 CUDA cores (tensor cores would break the rounding parity); the "
-                        "contract's enum is hbm|tensor, this kernel is neither"}
+                        "contract's enum is hbm|tensor, this kernel is neither: ncu shows the shared-memory data pipe at "
+                        "88.8 % of peak (profiles/r01_notes.md), DRAM traffic is 3.7 MB against 17.2 GFLOP"}
 
     # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
     cval, csec, cthreads = cpu_reference_knn(a, b, reps=3)
