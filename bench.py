@@ -218,6 +218,27 @@ def extras(dev, a, b, flush):
     x = ref[:4, :8192].contiguous(); y = qry[:4, :8192].contiguous()
     s = t(lambda: ops.chamfer(x, y))
     out["chamfer_c4_share"] = {"ms": s * 1e3, "tflops": 2 * 4 * 8192 * 8192 * FLOP_PER_PAIR / s / 1e12}
+    # C4 per-GPU share: FlowNet3D training step (train_sceneflow.py:132-185 in the reference), 4 pairs x 8192 points,
+    # BatchNorm in train mode, loss = chamfer(p1 + flow, p2), backward, Adam step
+    try:
+        from b200pc import pointinet, pytorch3d_shim as S3
+        torch.manual_seed(0)
+        net = pointinet.FlowNet3D().train().to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        p1 = ref[:4, :8192].transpose(1, 2).contiguous(); p2 = qry[:4, :8192].transpose(1, 2).contiguous()
+        f0 = torch.zeros(4, 3, 8192, device=dev)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            flow = net(p1, p2, f0, f0)
+            loss, _ = S3.chamfer_distance((p1 + flow).permute(0, 2, 1), p2.permute(0, 2, 1))
+            loss.backward()
+            opt.step()
+
+        s = t(train_step, n=5)
+        out["flownet3d_train_step_c4_share"] = {"ms": s * 1e3, "pairs_per_s": 4 / s, "batch": 4, "points": 8192}
+    except Exception as e:  # pragma: no cover
+        out["flownet3d_train_step_c4_share"] = {"error": repr(e)}
     return out
 
 

@@ -82,3 +82,53 @@ def test_graphed_pointinet_matches_eager(cuda_dev):
             got = g(*ins).clone()
             err = (got - want).abs().amax(dim=1).reshape(-1)
             assert (err < max(tol, 1e-6) * 50).float().mean() > 0.995, (fold, seed, float(err.max()))
+
+
+def test_flownet3d_training_step_gradients_match_cpu_port(cuda_dev):
+    """BASELINE config 4 in miniature (train_sceneflow.py:132-185 in the reference): FlowNet3D forward in
+    train mode, loss = chamfer(p1 + flow, p2), backward.  Gradients through index_points / three_interpolate /
+    chamfer_distance (custom ops) must match autograd through the torch port on CPU."""
+    from b200pc import pytorch3d_shim as S3
+    from oracle import ref_torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(2)
+    cpu_net = pointinet.FlowNet3D(cpu_backend.make()).train()
+    gpu_net = pointinet.FlowNet3D().train()
+    gpu_net.load_state_dict(cpu_net.state_dict())
+    gpu_net.to(cuda_dev)
+    a, b = synth.batch_pairs(8, 2, 2048)
+    p1 = torch.from_numpy(a).transpose(1, 2).contiguous(); p2 = torch.from_numpy(b).transpose(1, 2).contiguous()
+    f = torch.zeros(2, 3, 2048)
+    torch.manual_seed(9)
+    flow_c = cpu_net(p1, p2, f, f)
+    loss_c = ref_torch.chamfer_dense((p1 + flow_c).transpose(1, 2), p2.transpose(1, 2))
+    loss_c.backward()
+    torch.manual_seed(9)
+    d = lambda x: x.to(cuda_dev)
+    flow_g = gpu_net(d(p1), d(p2), d(f), d(f))
+    loss_g, _ = S3.chamfer_distance((d(p1) + flow_g).permute(0, 2, 1), d(p2).permute(0, 2, 1))
+    loss_g.backward()
+    assert abs(loss_g.item() - loss_c.item()) <= 1e-3 * abs(loss_c.item())
+    checked = 0
+    all_c, all_g = [], []
+    for (n, pc), (_, pg) in zip(cpu_net.named_parameters(), gpu_net.named_parameters()):
+        if pc.grad is None:
+            continue
+        # a conv bias directly in front of a train-mode BatchNorm has an exactly-zero true gradient (the batch
+        # mean removes it): both sides only hold cancellation noise there, nothing to compare
+        import re
+        if re.search(r"conv\d?\.(0|3|6)\.bias$", n) or n == "classifier.0.bias":
+            continue
+        gc, gg = pc.grad.reshape(-1), pg.grad.cpu().reshape(-1)
+        # ReLU / max-over-neighbours make the gradient piecewise: fp32 summation-order differences between cuDNN and
+        # MKL can flip an arg-max in the deep layers (train-mode BatchNorm over 256 samples), which moves a few entries
+        # by a visible amount.  So the per-tensor criterion is directional (cosine), the global one is tight.
+        cos = torch.dot(gc, gg) / (gc.norm() * gg.norm() + 1e-30)
+        assert cos.item() > 0.97, (n, cos.item())
+        all_c.append(gc); all_g.append(gg)
+        checked += 1
+    all_c, all_g = torch.cat(all_c), torch.cat(all_g)
+    assert (torch.dot(all_c, all_g) / (all_c.norm() * all_g.norm())).item() > 0.999
+    assert abs(all_c.norm().item() - all_g.norm().item()) <= 2e-2 * all_c.norm().item()
+    assert checked > 40
