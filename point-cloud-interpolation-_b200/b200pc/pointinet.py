@@ -88,6 +88,33 @@ def cuda_backend(tape=None):
     return be
 
 
+_SIDE_STREAMS = {}
+
+
+def _concurrently(first, second, ref_tensor, slot):
+    """run first() on the current stream and second() on a side stream forked BEFORE first() was enqueued, then join.
+    Python call order (hence the order of CPU-RNG draws) stays first -> second, exactly like the sequential reference;
+    on the device the two branches overlap (they are independent: e.g. the farthest-point sampling of frame 1 and of
+    frame 2, each of which occupies one 8-SM cluster for ~0.6 ms).  Under CUDA-graph capture the fork/join becomes
+    two parallel branches of the graph.  CPU tensors and eager (non-captured) calls: plain sequential calls."""
+    if not ref_tensor.is_cuda or not torch.cuda.is_current_stream_capturing():
+        return first(), second()      # eager calls are bound by Python dispatch: forking only adds host work there
+    dev = ref_tensor.device
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, cur.cuda_stream, slot)
+    side = _SIDE_STREAMS.get(key)
+    if side is None:
+        side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    a = first()
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        b = second()
+    cur.wait_stream(side)
+    return a, b      # the caller keeps both results alive until it returns, so no block is recycled across streams early
+
+
 def _pointwise_mlp(channels):
     """[Conv2d 1x1, BatchNorm2d(eps=1e-3), ReLU] * len -- the block every FlowNet3D layer uses."""
     mods = []
@@ -184,10 +211,15 @@ class FlowNet3D(nn.Module):
 
     def forward(self, xyz1, xyz2, feats1, feats2):
         """[B,3,N] x4 -> flow [B,3,N] from frame 1 to frame 2."""
-        p1a, f1a = self.set_conv1(xyz1, feats1)
-        p1b, f1b = self.set_conv2(p1a, f1a)
-        p2a, f2a = self.set_conv1(xyz2, feats2)
-        p2b, f2b = self.set_conv2(p2a, f2a)
+        def cloud1():
+            pa, fa = self.set_conv1(xyz1, feats1)
+            return (pa, fa) + self.set_conv2(pa, fa)
+
+        def cloud2():
+            pa, fa = self.set_conv1(xyz2, feats2)
+            return (pa, fa) + self.set_conv2(pa, fa)
+
+        (p1a, f1a, p1b, f1b), (p2a, f2a, p2b, f2b) = _concurrently(cloud1, cloud2, xyz1, "clouds")
         emb = self.flow_embedding(p1b, p2b, f1b, f2b)
         p1c, f1c = self.set_conv3(p1b, emb)
         p1d, f1d = self.set_conv4(p1c, f1c)
@@ -250,8 +282,8 @@ class PointINet(nn.Module):
         extra1, extra2 = points1[:, 3:].contiguous(), points2[:, 3:].contiguous()
         xyz1, xyz2 = points1[:, :3].contiguous(), points2[:, :3].contiguous()
         with torch.no_grad():
-            fwd = self.flow(xyz1, xyz2, features1, features2)
-            bwd = self.flow(xyz2, xyz1, features2, features1)
+            fwd, bwd = _concurrently(lambda: self.flow(xyz1, xyz2, features1, features2),
+                                     lambda: self.flow(xyz2, xyz1, features2, features1), xyz1, "flows")
         tt = t.view(-1, 1, 1)
         return self.fusion(xyz1 + fwd * tt, xyz2 + bwd * (1 - tt), extra1, extra2, 32, tt, t_host)
 
