@@ -117,33 +117,6 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
-// same, for a thread that has nothing else to do (the TMA producer): sleep between probes so the
-// spin does not steal issue slots from the compute warps of its SM sub-partition.
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P1;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
-}
-// shared-memory 128-bit load that the compiler may not sink towards its use (keeps the software
-// pipeline of the search hot loop intact)
-__device__ __forceinline__ float4 lds128(const float4 *p) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "r"(smem_u32(p)));
-    return r;
-}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

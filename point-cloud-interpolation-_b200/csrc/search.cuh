@@ -26,7 +26,6 @@ struct SearchPlan {
 bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *plan);
 
 // Top-k search: idx [B,S,k] int64 and/or dist [B,S,k] (either may be null, not both).
-// extra outputs for fused consumers: idx32 [B,S,k] int32 (may be null).
 int run_topk(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx, float *dist,
              void *ws, size_t ws_bytes, cudaStream_t st);
 

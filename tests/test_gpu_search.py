@@ -32,6 +32,7 @@ CASES = [
     (2, 1024, 256, 8),      # SetUpConv 1024 x 256 (refs = 256 in the model; both orientations are small-path shapes)
     (1, 700, 5000, 16),     # small refs, many queries: the planner keeps the streaming kernel
     (1, 1024, 64, 100),     # large k on the warp-per-query path
+    (1, 4096, 300, 128),    # large k on the streaming kernel (SA-MSG style nsample 128)
 ]
 
 
@@ -106,6 +107,7 @@ BALL_CASES = [
     (2, 4096, 4096, 1.0, 32),
     (1, 999, 333, 0.3, 16),
     (1, 3000, 500, 0.1, 32),   # ISAPCI SA-MSG radius: mostly tiny / empty balls
+    (1, 8192, 700, 3.0, 128),  # nsample 128, dense balls
 ]
 
 
