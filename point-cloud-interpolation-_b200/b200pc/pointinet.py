@@ -257,8 +257,8 @@ class PointsFusion(nn.Module):
             sel2 = rp(N, n2, xyz1.device)
             a, b = xyz1[i:i + 1], xyz2[i:i + 1]
             mixed = torch.cat((a[:, :, sel1], b[:, :, sel2]), dim=-1)
-            f1, g1, e1 = self._neighbours(mixed, a, feats1[i:i + 1], k1)
-            f2, g2, e2 = self._neighbours(mixed, b, feats2[i:i + 1], k2)
+            (f1, g1, e1), (f2, g2, e2) = _concurrently(lambda: self._neighbours(mixed, a, feats1[i:i + 1], k1),
+                                                     lambda: self._neighbours(mixed, b, feats2[i:i + 1], k2), mixed, "fusion")
             fa.append(torch.cat((f1, f2), dim=-1)); ga.append(torch.cat((g1, g2), dim=-1)); ea.append(torch.cat((e1, e2), dim=-1))
         feat, grouped, extra = torch.cat(fa, 0), torch.cat(ga, 0), torch.cat(ea, 0)
         w = F.softmax(self.conv(feat).max(dim=1)[0], dim=-1)               # [B,N,2k]
