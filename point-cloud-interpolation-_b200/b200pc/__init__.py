@@ -12,7 +12,7 @@ no CPU fallback (a missing library or a CPU tensor raises).
 """
 from . import _lib  # noqa: F401  (no dlopen at import)
 
-__all__ = ["pointnet2_utils", "pytorch3d_shim", "dropin", "ops", "synth"]
+__all__ = ["pointnet2_utils", "pytorch3d_shim", "dropin", "ops", "synth", "dist", "hostio", "pointinet"]
 __version__ = "0.1.0"
 
 

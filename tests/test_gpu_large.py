@@ -83,3 +83,15 @@ def test_host_pointer_abi_wrappers(cuda_dev):
     start = np.array([3, 1400], np.int64); fps = np.empty((2, 100), np.int64)
     _lib.check(lib.b200pc_fps_host(p(a), 2, 1500, 100, p(start), p(fps)))
     np.testing.assert_array_equal(fps, strict.farthest_point_sample(a, 100, start))
+
+
+def test_hostio_pipelined_knn_equals_plain(cuda_dev):
+    from b200pc import hostio
+    a, b = synth.batch_pairs(330, 5, 3000)
+    h_ref = torch.from_numpy(a).pin_memory(); h_qry = torch.from_numpy(b[:, :1111].copy()).pin_memory()
+    for chunks in (1, 2, 3):
+        out = hostio.knn_point_host(16, h_ref, h_qry, device=cuda_dev, chunks=chunks)
+        ball = hostio.query_ball_point_host(1.0, 8, h_ref, h_qry, device=cuda_dev, chunks=chunks)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.numpy(), strict.knn_point(16, a, b[:, :1111]))
+        np.testing.assert_array_equal(ball.numpy(), strict.query_ball_point(1.0, 8, a, b[:, :1111]))
