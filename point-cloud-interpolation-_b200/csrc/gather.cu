@@ -137,11 +137,13 @@ __device__ __forceinline__ float mix3(float a, float wa, float b, float wb, floa
 }
 
 // warp per dense row, ROWS rows in flight: lanes < 3*ROWS read the row's three (index, weight) pairs once
-// and shuffle them; every lane then has 3*ROWS independent 16-byte gathers outstanding.
+// and shuffle them; every lane then has 3*ROWS independent 16-byte gathers outstanding.  Row offsets are kept
+// as 32-bit vector indices (the launcher checks B*S*C4 < 2^31) and the register budget is capped so that at
+// least 3 CTAs stay resident: the kernel is a latency chain (idx -> gather -> store), occupancy is what feeds it.
 template <int ROWS>
-__global__ void __launch_bounds__(256) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
-                                                          const float *__restrict__ w, int S, int C4, long N, long rows_total,
-                                                          float4 *__restrict__ out) {
+__global__ void __launch_bounds__(256, 3) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                             const float *__restrict__ w, int S, int C4, long N, long rows_total,
+                                                             float4 *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) interp_rows_kernel(const float4 *__restri
         if (lane < 3 * ROWS && row < rows_total) { i_next = idx[row * 3 + lane % 3]; w_next = w[row * 3 + lane % 3]; }
     }
     for (long r0 = warp * ROWS; r0 < rows_total; r0 += nwarps * ROWS) {
-        long src = 0;
+        int src = 0;
         const float wt = w_next;
         const long i_cur = i_next;
         {
@@ -162,9 +164,9 @@ __global__ void __launch_bounds__(256) interp_rows_kernel(const float4 *__restri
         }
         if (lane < 3 * ROWS) {                          // lane = 3*u + j  ->  neighbour j of row r0+u
             const long row = r0 + lane / 3;
-            if (row < rows_total) src = ((row / N) * S + i_cur) * C4;
+            if (row < rows_total) src = (int)(((row / N) * S + i_cur) * C4);
         }
-        long so[ROWS][3];                                // every lane takes part in the shuffles
+        int so[ROWS][3];                                 // every lane takes part in the shuffles
         float ww[ROWS][3];
 #pragma unroll
         for (int u = 0; u < ROWS; ++u)
@@ -313,10 +315,10 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
     B200PC_REQUIRE(feat && idx && weight && out, "three_interpolate: null pointer");
     if (B == 0 || N == 0) return B200PC_OK;
     cudaStream_t st = as_stream(stream);
-    if (C % 4 == 0 && aligned16(feat) && aligned16(out)) {
+    if (C % 4 == 0 && aligned16(feat) && aligned16(out) && (long)B * S * (C / 4) < (1L << 31)) {
         const long rows = (long)B * N;
         const char *tune = getenv("B200PC_INTERP_ROWS");   // tuning override (not part of the ABI)
-        const int rw = tune ? atoi(tune) : 4;
+        const int rw = tune ? atoi(tune) : 2;
         const float4 *f4 = reinterpret_cast<const float4 *>(feat);
         float4 *o4 = reinterpret_cast<float4 *>(out);
         if (rw == 8) interp_rows_kernel<8><<<wave_grid(rows * 32 / 8, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
