@@ -73,11 +73,31 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
     // that lanes re-visiting DIFFERENT chunks in the drain spread over the banks instead of all starting at
     // bank 0 (measured: 11.4 wavefronts per LDS.128 without the swizzle).  The hot loop takes a min over the
     // whole chunk, so the order of the pairs inside a chunk does not matter to it.
-    const int chunk = p >> 2, slot = (p & 3) ^ (chunk & 3);
+    const int chunk = p >> 2;
+    if (form == B200PC_FORM_DIRECT) {
+        // the direct form needs no norm word: 24 bytes per pair, a chunk is 6 records
+        // [A0 A1 Z01 A2 A3 Z23] with A = {x0,x1,y0,y1} and Z = {z0,z1 of the first pair, z0,z1 of the second}
+        // (6 instead of 8 LDS.128 per chunk in the hot loop).  96-byte chunks rotate over the banks by themselves.
+        const int pc = p & 3;
+        float4 *base = packed + ((size_t)b * (n_pad / 8) + chunk) * 6 + (pc >> 1) * 3;
+        base[pc & 1] = make_float4(x[0], x[1], y[0], y[1]);
+        float2 *zz = reinterpret_cast<float2 *>(base + 2) + (pc & 1);
+        *zz = make_float2(z[0], z[1]);
+        return;
+    }
+    const int slot = (p & 3) ^ (chunk & 3);
     float4 *o = packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2;
     o[0] = make_float4(x[0], x[1], y[0], y[1]);
     o[1] = make_float4(z[0], z[1], w[0], w[1]);
 }
+
+// shared-memory layout of a chunk (8 refs) per distance form
+template <int FORM>
+struct Lay {
+    static constexpr int HREC = FORM == B200PC_FORM_DIRECT ? 3 : 4;   // 16-byte records per half chunk (4 refs)
+    static constexpr int REC = 2 * HREC;                               // per chunk
+    static constexpr int TILE_COPY = (TILE / 8) * REC * 16;            // bytes one tile occupies in the packed stream
+};
 
 // ---------------------------------------------------------------------------------------------
 // 2. distance of one query against a PAIR of refs, in the reference's rounding order
@@ -143,24 +163,47 @@ __device__ __forceinline__ float prefilter_threshold(float tau, float nq) {
     return (tau - nq) + (2.0f * fabsf(tau) + fabsf(nq)) * 1.1920929e-7f;
 }
 
-template <int FORM>
-__device__ __forceinline__ float chunk_min(const float4 (&A)[4], const float4 (&Bv)[4], const QueryConst &q) {
-    float d[8];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) unpack2(pair_prefilter<FORM>(A[p], Bv[p], q), d[2 * p], d[2 * p + 1]);
-    float m0 = min3(d[0], d[1], d[2]);
-    float m1 = min3(d[3], d[4], d[5]);
-    float m2 = min3(d[6], d[7], m0);
-    return fminf(m1, m2);
+__device__ __forceinline__ f32x2 pair_dist_direct(const float4 &A, f32x2 Z, const QueryConst &q) {
+    // pytorch3d: d = fma(dz,dz, fma(dy,dy, dx*dx)); (r-q)^2 == (q-r)^2 bit for bit
+    const f32x2 dx = add2(pack2(A.x, A.y), q.a0), dy = add2(pack2(A.z, A.w), q.a1), dz = add2(Z, q.a2);
+    f32x2 t = mul2(dx, dx);
+    t = fma2(dy, dy, t);
+    return fma2(dz, dz, t);
 }
 
-// min over the 4 refs held in two pair records (half a chunk)
+// prefilter value of the 4 refs of half a chunk given its HREC records -> min of the four
 template <int FORM>
-__device__ __forceinline__ float half_chunk_min(const float4 (&H)[4], const QueryConst &q) {
+__device__ __forceinline__ float half_chunk_min(const float4 (&H)[Lay<FORM>::HREC], const QueryConst &q) {
     float d0, d1, d2, d3;
-    unpack2(pair_prefilter<FORM>(H[0], H[1], q), d0, d1);
-    unpack2(pair_prefilter<FORM>(H[2], H[3], q), d2, d3);
+    if (FORM == B200PC_FORM_DIRECT) {
+        unpack2(pair_dist_direct(H[0], pack2(H[2].x, H[2].y), q), d0, d1);
+        unpack2(pair_dist_direct(H[1], pack2(H[2].z, H[2].w), q), d2, d3);
+    } else {
+        unpack2(pair_prefilter<FORM>(H[0], H[Lay<FORM>::HREC - 3], q), d0, d1);
+        unpack2(pair_prefilter<FORM>(H[Lay<FORM>::HREC - 2], H[Lay<FORM>::HREC - 1], q), d2, d3);
+    }
     return fminf(min3(d0, d1, d2), d3);
+}
+
+template <int FORM>
+__device__ __forceinline__ float chunk_min(const float4 (&R)[Lay<FORM>::REC], const QueryConst &q) {
+    constexpr int H = Lay<FORM>::HREC;
+    float4 lo[H], hi[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) { lo[i] = R[i]; hi[i] = R[H + i]; }
+    return fminf(half_chunk_min<FORM>(lo, q), half_chunk_min<FORM>(hi, q));
+}
+
+// exact distances of logical pair p (refs 2p, 2p+1) of a chunk whose records start at `cb` (drain path)
+template <int FORM>
+__device__ __forceinline__ f32x2 chunk_pair_dist(const float4 *cb, int chunk, int p, const QueryConst &q) {
+    if (FORM == B200PC_FORM_DIRECT) {
+        const float4 *h = cb + (p >> 1) * 3;
+        const float4 Z = h[2];
+        return pair_dist_direct(h[p & 1], (p & 1) ? pack2(Z.z, Z.w) : pack2(Z.x, Z.y), q);
+    }
+    const float4 *pp = cb + 2 * (p ^ (chunk & 3));       // un-swizzle: where pair p of this chunk lives
+    return pair_dist<FORM>(pp[0], pp[1], q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -228,9 +271,8 @@ constexpr int CAND_CAP = 32;  // per-query buffer: one u16 entry (chunk << 8 | c
 template <int FORM>
 __device__ __forceinline__ float tile_dist(const float4 *tp, int off, const QueryConst &q) {
     float lo, hi;
-    const int chunk = off >> 3, slot = ((off >> 1) & 3) ^ (chunk & 3);     // un-swizzle: where pair (off>>1) lives
-    const float4 *pp = tp + chunk * 8 + slot * 2;
-    unpack2(pair_dist<FORM>(pp[0], pp[1], q), lo, hi);   // same packed arithmetic as the hot loop
+    const int chunk = off >> 3;
+    unpack2(chunk_pair_dist<FORM>(tp + chunk * Lay<FORM>::REC, chunk, (off >> 1) & 3, q), lo, hi);   // same packed arithmetic as the hot loop
     return (off & 1) ? hi : lo;
 }
 
@@ -262,7 +304,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
     const int tile1 = min(tile0 + P.tiles_per_split, P.n_pad / TILE);
     const int ntiles = tile1 - tile0;
     const int k = P.k;
-    const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * P.n_pad + (size_t)tile0 * TILE) * 16;
+    constexpr int REC = Lay<FORM>::REC, HREC = Lay<FORM>::HREC, TCOPY = Lay<FORM>::TILE_COPY;
+    const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * (P.n_pad / TILE) + (size_t)tile0) * TCOPY;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -273,8 +316,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
         mbar_fence_init();
         const int pre = ntiles < STAGES ? ntiles : STAGES;
         for (int t = 0; t < pre; ++t) {
-            mbar_expect_tx(bar_base + 8 * t, TILE_BYTES);
-            bulk_g2s(smem_u32(smem + t * TILE_BYTES), src + (size_t)t * TILE_BYTES, TILE_BYTES, bar_base + 8 * t);
+            mbar_expect_tx(bar_base + 8 * t, TCOPY);
+            bulk_g2s(smem_u32(smem + t * TILE_BYTES), src + (size_t)t * TCOPY, TCOPY, bar_base + 8 * t);
         }
         *issued = pre;
     }
@@ -328,59 +371,55 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
             uint32_t mask[Q][2];
 #pragma unroll
             for (int j = 0; j < Q; ++j) { mask[j][0] = 0u; mask[j][1] = 0u; }
-            const float4 *cp = tp + c * CHUNK;
+            const float4 *cp = tp + c * REC;
             // register double buffer: records are requested ahead of their use and a warp-level memory barrier
             // pins those loads above the math of the current group, so the shared-memory latency is covered
-            // (without it ptxas sinks every LDS next to its first use).  Q=2: a whole chunk (8 records) ahead;
-            // Q=1: half a chunk (4 records) ahead, which keeps the kernel under 72 registers so that twice as
-            // many warps stay resident.
+            // (without it ptxas sinks every LDS next to its first use).  Q=2: a whole chunk ahead; Q=1: half a
+            // chunk ahead, which keeps the kernel under 72 registers so that twice as many warps stay resident.
             if (Q >= 2) {
-                float4 R[8];
+                float4 R[REC];
 #pragma unroll
-                for (int p = 0; p < 8; ++p) R[p] = cp[p];
+                for (int p = 0; p < REC; ++p) R[p] = cp[p];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
                     uint32_t bit = 1u;
                     for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
-                        cp += CHUNK;   // one chunk past the tile end is still inside the ring / barrier block: harmless
-                        float4 Nx[8];
+                        cp += REC;     // one chunk past the tile end is still inside the ring / barrier block: harmless
+                        float4 Nx[REC];
 #pragma unroll
-                        for (int p = 0; p < 8; ++p) Nx[p] = cp[p];
+                        for (int p = 0; p < REC; ++p) Nx[p] = cp[p];
                         __syncwarp();
-                        float4 A[4], Bv[4];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) { A[p] = R[2 * p]; Bv[p] = R[2 * p + 1]; }
 #pragma unroll
                         for (int j = 0; j < Q; ++j) {
-                            const float m = chunk_min<FORM>(A, Bv, qc[j]);
+                            const float m = chunk_min<FORM>(R, qc[j]);
                             const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
                             if (hit) mask[j][half] |= bit;
                         }
 #pragma unroll
-                        for (int p = 0; p < 8; ++p) R[p] = Nx[p];
+                        for (int p = 0; p < REC; ++p) R[p] = Nx[p];
                     }
                 }
             } else {
-                float4 H[4];
+                float4 H[HREC];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) H[p] = cp[p];
+                for (int p = 0; p < HREC; ++p) H[p] = cp[p];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
                     uint32_t bit = 1u;
                     for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
-                        float4 N1[4];
+                        float4 N1[HREC];
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) N1[p] = cp[4 + p];
+                        for (int p = 0; p < HREC; ++p) N1[p] = cp[HREC + p];
                         __syncwarp();
                         float ma[Q];
 #pragma unroll
                         for (int j = 0; j < Q; ++j) ma[j] = half_chunk_min<FORM>(H, qc[j]);
-                        cp += CHUNK;
-                        float4 N2[4];
+                        cp += REC;
+                        float4 N2[HREC];
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) N2[p] = cp[p];
+                        for (int p = 0; p < HREC; ++p) N2[p] = cp[p];
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < Q; ++j) {
@@ -389,7 +428,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                             if (hit) mask[j][half] |= bit;
                         }
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) H[p] = N2[p];
+                        for (int p = 0; p < HREC; ++p) H[p] = N2[p];
                     }
                 }
             }
@@ -411,14 +450,10 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                                 int cc;
                                 if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
                                 else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
-                                const float4 *dp = tp + (c + cc) * CHUNK;
-                                const int sw = (c + cc) & 3;
+                                const float4 *dp = tp + (c + cc) * REC;
                                 float d[8];
 #pragma unroll
-                                for (int p = 0; p < 4; ++p) {
-                                    const float4 *pp = dp + 2 * (p ^ sw);
-                                    unpack2(pair_dist<FORM>(pp[0], pp[1], qc[j]), d[2 * p], d[2 * p + 1]);
-                                }
+                                for (int p = 0; p < 4; ++p) unpack2(chunk_pair_dist<FORM>(dp, c + cc, p, qc[j]), d[2 * p], d[2 * p + 1]);
                                 uint32_t cm = 0u;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) cm |= (d[i] < tau[j]) ? (1u << i) : 0u;
@@ -455,14 +490,10 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                             if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
                             else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
                             const int off0 = (c + cc) * CHUNK;
-                            const float4 *dp = tp + off0;
-                            const int sw = (c + cc) & 3;
+                            const float4 *dp = tp + (c + cc) * REC;
                             float d[8];
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) {
-                                const float4 *pp = dp + 2 * (p ^ sw);
-                                unpack2(pair_dist<FORM>(pp[0], pp[1], qc[j]), d[2 * p], d[2 * p + 1]);
-                            }
+                            for (int p = 0; p < 4; ++p) unpack2(chunk_pair_dist<FORM>(dp, c + cc, p, qc[j]), d[2 * p], d[2 * p + 1]);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 if (d[i] <= tau[j] && cnt[j] < k) { list[cnt[j] * QPB] = tile_ref0 + off0 + i; ++cnt[j]; }
@@ -482,8 +513,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
             const int nxt = t + STAGES;                 // the tile that will reuse this stage
             if (nxt < ntiles && mbar_test(ebar, (t / STAGES) & 1)) {
                 if (atomicCAS(issued, nxt, nxt + 1) == nxt) {
-                    mbar_expect_tx(bar_base + 8 * s, TILE_BYTES);
-                    bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)nxt * TILE_BYTES, TILE_BYTES, bar_base + 8 * s);
+                    mbar_expect_tx(bar_base + 8 * s, TCOPY);
+                    bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)nxt * TCOPY, TCOPY, bar_base + 8 * s);
                 }
             }
         }
