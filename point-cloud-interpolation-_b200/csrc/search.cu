@@ -7,23 +7,30 @@
 //   * pytorch3d knn_points   Utils/Layers.py:220 ...        form 2, top-K   (also Chamfer, K=1)
 //   * query_ball_point       Utils/Pointnet2Utils.py:88-108 form 1, first-nsample-by-index
 //
-// Design (why it looks the way it does is argued in DESIGN.md):
+// Design (the measurements behind each choice are in DESIGN.md and profiles/):
 //   1. pack_refs_kernel turns refs [B,N,3] into 16-byte records grouped in PAIRS:
-//      {x0,x1,y0,y1} {z0,z1,w0,w1} (w = |r|^2 rounded as torch does, or 0 for the direct form),
-//      padded to a whole tile with records whose distance is +inf; the 4 pairs of a chunk are
-//      XOR-swizzled by the chunk number so that the drain's per-lane re-reads avoid bank conflicts.
-//   2. search_kernel: one TMA-producer warp streams 8 KB tiles of those records into a 4-stage
-//      shared-memory ring with cp.async.bulk + mbarrier; consumer threads own Q queries each and
-//      evaluate 2 refs per instruction with FFMA2/FMUL2/FADD2 in EXACTLY the reference's rounding
-//      order.  The refs of a tile are read with broadcast LDS.128 (no bank conflicts).
-//   3. The per-pair cost is kept at "distance + half a min": a chunk of 8 refs is reduced with
-//      FMNMX3 and compared once against the query's current threshold tau; a hit only sets a bit
-//      in a register mask.  There is no branch and no list traffic in the hot loop.
-//   4. After at most 32 chunks the mask is drained: hit chunks are re-evaluated (bit-identical
-//      arithmetic) and true candidates are insertion-sorted into a per-query list that lives in
-//      shared memory, laid out [rank][query] so that lanes never conflict.  Refs are visited in
-//      increasing index order and insertion uses strict '<', which yields the total order
-//      (distance, index): ties go to the lower index, deterministically.
+//      {x0,x1,y0,y1} {z0,z1,w0,w1} with w = |r|^2 (1 - 20 eps), padded to a whole 512-ref tile with records that can
+//      never be selected; the 4 pairs of an 8-ref chunk are XOR-swizzled by the chunk number so that
+//      lanes re-visiting different chunks spread over the banks.
+//   2. search_kernel: 8 KB tiles stream through a 3-stage shared-memory ring (cp.async.bulk + mbarrier;
+//      no producer warp: the warp that releases a stage last refills it).  Every thread OWNS Q queries:
+//      their k-best heap lives in shared memory and their threshold tau in a register.
+//   3. FILTER.  The prefilter value of a (query, ref) pair is
+//          u = fma(z, -2qz, fma(y, -2qy, fma(x, -2qx, |r|^2)))       (3 packed FFMA2 per two refs)
+//      which differs from the reference's rounded distance minus |q|^2 by a bounded rounding error, so
+//      "u < thr" with thr = (tau - |q|^2) + margin is a CONSERVATIVE test for "distance < tau" in all
+//      three reference roundings (filter_threshold derives the margin).  Lane l of a warp keeps chunk
+//      c0+l (8 refs) in registers, the warp's 32*Q queries are broadcast one LDS.128 at a time from
+//      their shared-memory records {-2qx,-2qy,-2qz,thr}, 8 values are reduced with FMNMX3 and compared
+//      once; the ballot of query i is exactly the 32-chunk hit mask lane i needs.  No branch, no list
+//      traffic, and one broadcast load feeds 32 x 8 pairs, which keeps the loop on the FMA pipe instead
+//      of the shared-memory pipe.  (The first half tile of a ref range uses the mirrored form -- queries
+//      in registers, chunks broadcast -- with a drain after 2,2,4,8,16 chunks so that tau tightens fast.)
+//   4. DRAIN, once per tile and warp-synchronous: hit chunks are re-tested ref by ref (phase 1), the
+//      survivors are evaluated with EXACTLY the reference's arithmetic and rounding order and, if they
+//      beat tau, sifted into the query's max-heap of 64-bit keys (order_key(d) << 32 | index), laid out
+//      [rank][query] so that lanes never conflict (phase 2).  The key realises the total order
+//      (distance, index): ties go to the lower index whatever the visiting order.
 //   5. When there are too few queries to fill 148 SMs the ref range is split over gridDim.z and
 //      a small merge kernel combines the partial lists.
 #include "search.cuh"
@@ -38,6 +45,7 @@ constexpr int TILE = 512;                  // refs per shared-memory tile
 constexpr int TILE_BYTES = TILE * 16;      // 8 KB
 constexpr int STAGES = 3;                  // ring depth
 constexpr int CHUNK = 8;                   // refs per threshold test
+constexpr int REC = 8;                     // 16-byte records per chunk
 constexpr int CHUNKS_PER_TILE = TILE / CHUNK;
 constexpr int MAX_SPLIT = 32;
 constexpr int BAR_BYTES = 128;
@@ -50,59 +58,41 @@ __device__ __forceinline__ float torch_sq_norm(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 
-__global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad, int form,
-                                 float4 *__restrict__ packed) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+// The filter's norm word is |r|^2 deflated by 20 eps: that is the ref's share of the filter's rounding margin
+// (filter_threshold), folded into the data so that it scales with THIS ref's magnitude instead of a global bound.
+__device__ __forceinline__ float filter_norm(float w) { return __fmul_rn(w, 1.0f - 20.0f * 5.9604645e-8f); }
+
+__global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad, float4 *__restrict__ packed) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
     if (p >= n_pad / 2) return;
-    int b = blockIdx.y;
+    const int b = blockIdx.y;
     const float *r = ref + (size_t)b * N * 3;
     float x[2], y[2], z[2], w[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        int i = 2 * p + h;
+        const int i = 2 * p + h;
         if (i < N) {
             x[h] = r[i * 3 + 0]; y[h] = r[i * 3 + 1]; z[h] = r[i * 3 + 2];
-            w[h] = form == B200PC_FORM_DIRECT ? 0.0f : torch_sq_norm(x[h], y[h], z[h]);
-        } else if (form == B200PC_FORM_DIRECT) {
-            x[h] = CUDART_INF_F; y[h] = 0.0f; z[h] = 0.0f; w[h] = 0.0f;   // (inf - q)^2 = inf
+            w[h] = filter_norm(torch_sq_norm(x[h], y[h], z[h]));
         } else {
-            x[h] = 0.0f; y[h] = 0.0f; z[h] = 0.0f; w[h] = CUDART_INF_F;   // 0 + inf = inf
+            // padding: the filter sees u = +inf or NaN (never a hit); every exact form gives +inf or NaN (never selected)
+            x[h] = CUDART_INF_F; y[h] = 0.0f; z[h] = 0.0f; w[h] = CUDART_INF_F;
         }
     }
     // a chunk = 4 pairs = 128 bytes = all 32 banks.  Pair q of chunk c is stored in pair-slot q ^ (c & 3), so
     // that lanes re-visiting DIFFERENT chunks in the drain spread over the banks instead of all starting at
-    // bank 0 (measured: 11.4 wavefronts per LDS.128 without the swizzle).  The hot loop takes a min over the
-    // whole chunk, so the order of the pairs inside a chunk does not matter to it.
-    const int chunk = p >> 2;
-    if (form == B200PC_FORM_DIRECT) {
-        // the direct form needs no norm word: 24 bytes per pair, a chunk is 6 records
-        // [A0 A1 Z01 A2 A3 Z23] with A = {x0,x1,y0,y1} and Z = {z0,z1 of the first pair, z0,z1 of the second}
-        // (6 instead of 8 LDS.128 per chunk in the hot loop).  96-byte chunks rotate over the banks by themselves.
-        const int pc = p & 3;
-        float4 *base = packed + ((size_t)b * (n_pad / 8) + chunk) * 6 + (pc >> 1) * 3;
-        base[pc & 1] = make_float4(x[0], x[1], y[0], y[1]);
-        float2 *zz = reinterpret_cast<float2 *>(base + 2) + (pc & 1);
-        *zz = make_float2(z[0], z[1]);
-        return;
-    }
-    const int slot = (p & 3) ^ (chunk & 3);
+    // bank 0 (measured: 11.4 wavefronts per LDS.128 without the swizzle).  The filters take a min over the
+    // whole chunk, so the order of the pairs inside a chunk does not matter to them.
+    const int chunk = p >> 2, slot = (p & 3) ^ (chunk & 3);
     float4 *o = packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2;
     o[0] = make_float4(x[0], x[1], y[0], y[1]);
     o[1] = make_float4(z[0], z[1], w[0], w[1]);
 }
 
-// shared-memory layout of a chunk (8 refs) per distance form
-template <int FORM>
-struct Lay {
-    static constexpr int HREC = FORM == B200PC_FORM_DIRECT ? 3 : 4;   // 16-byte records per half chunk (4 refs)
-    static constexpr int REC = 2 * HREC;                               // per chunk
-    static constexpr int TILE_COPY = (TILE / 8) * REC * 16;            // bytes one tile occupies in the packed stream
-};
-
 // ---------------------------------------------------------------------------------------------
-// 2. distance of one query against a PAIR of refs, in the reference's rounding order
+// 2. distance forms.  SURVEY.md Appendix A: the reference's three roundings of |a-b|^2.
 // ---------------------------------------------------------------------------------------------
-struct QueryConst {  // per-query splatted constants
+struct QueryConst {  // per-query splatted constants of the EXACT evaluation
     f32x2 a0, a1, a2, a3;
 };
 
@@ -110,7 +100,7 @@ template <int FORM>
 __device__ __forceinline__ QueryConst make_query(float x, float y, float z) {
     QueryConst q;
     if (FORM == B200PC_FORM_DIRECT) {
-        q.a0 = splat2(-x); q.a1 = splat2(-y); q.a2 = splat2(-z); q.a3 = 0ull;
+        q.a0 = splat2(-x); q.a1 = splat2(-y); q.a2 = splat2(-z); q.a3 = splat2(torch_sq_norm(x, y, z));   // a3: filter only
     } else {
         // -2*(s.d) == s.(-2d) exactly: scaling by a power of two commutes with every rounding
         q.a0 = splat2(-2.0f * x); q.a1 = splat2(-2.0f * y); q.a2 = splat2(-2.0f * z);
@@ -119,6 +109,7 @@ __device__ __forceinline__ QueryConst make_query(float x, float y, float z) {
     return q;
 }
 
+// exact distances of the two refs of a pair, bit for bit what the reference computes
 template <int FORM>
 __device__ __forceinline__ f32x2 pair_dist(const float4 &A, const float4 &Bv, const QueryConst &q) {
     f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w), Z = pack2(Bv.x, Bv.y);
@@ -129,8 +120,11 @@ __device__ __forceinline__ f32x2 pair_dist(const float4 &A, const float4 &Bv, co
         t = fma2(dy, dy, t);
         return fma2(dz, dz, t);
     }
-    // torch CPU (MKL sgemm, K=3): dot = fma(z,z', fma(y,y', x*x')); then two separate adds
-    f32x2 W = pack2(Bv.z, Bv.w);
+    // torch CPU (MKL sgemm, K=3): dot = fma(z,z', fma(y,y', x*x')); then two separate adds.  |r|^2 is rebuilt with
+    // torch's rounding, (xx + yy) + zz unfused -- the record's norm word is the deflated filter copy.  Scalar
+    // __fmul_rn/__fadd_rn on purpose: ptxas 12.9 CONTRACTS mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 (seen in
+    // the SASS, and in 32 failing parity tests), which the scalar .rn forms are guaranteed never to be.
+    const f32x2 W = pack2(torch_sq_norm(A.x, A.z, Bv.x), torch_sq_norm(A.y, A.w, Bv.y));
     f32x2 t = mul2(X, q.a0);
     t = fma2(Y, q.a1, t);
     t = fma2(Z, q.a2, t);
@@ -143,65 +137,48 @@ __device__ __forceinline__ f32x2 pair_dist(const float4 &A, const float4 &Bv, co
     }
 }
 
-// Hot-loop variant.  At the kNN call site (form 0) the query norm is the LAST addend and is constant
-// per query, so the prefilter ranks on t = fl(dot' + |r|^2) and skips that add; the threshold it is
-// compared with is moved into t-space conservatively (prefilter_threshold), and the drain re-tests the
-// exact distance, so results are unchanged -- the hot loop just does 4 packed instructions instead of 5.
-template <int FORM>
-__device__ __forceinline__ f32x2 pair_prefilter(const float4 &A, const float4 &Bv, const QueryConst &q) {
-    if (FORM != B200PC_FORM_REF_NORM_FIRST) return pair_dist<FORM>(A, Bv, q);
-    f32x2 X = pack2(A.x, A.y), Y = pack2(A.z, A.w), Z = pack2(Bv.x, Bv.y), W = pack2(Bv.z, Bv.w);
-    f32x2 t = mul2(X, q.a0);
-    t = fma2(Y, q.a1, t);
-    t = fma2(Z, q.a2, t);
-    return add2(t, W);
+// Filter value of the two refs of a pair: u ~= |r|^2 - 2 q.r, three packed FMAs (b0..b2 = -2q splatted).
+__device__ __forceinline__ f32x2 pair_u(const float4 &A, const float4 &Bv, f32x2 b0, f32x2 b1, f32x2 b2) {
+    f32x2 t = fma2(pack2(A.x, A.y), b0, pack2(Bv.z, Bv.w));
+    t = fma2(pack2(A.z, A.w), b1, t);
+    return fma2(pack2(Bv.x, Bv.y), b2, t);
 }
-// every t with fl(t + nq) < tau satisfies t < (tau - nq) + (2|tau| + |nq|) * 2^-24; one more bit of margin
-template <int FORM>
-__device__ __forceinline__ float prefilter_threshold(float tau, float nq) {
-    if (FORM != B200PC_FORM_REF_NORM_FIRST) return tau;
-    return (tau - nq) + (2.0f * fabsf(tau) + fabsf(nq)) * 1.1920929e-7f;
-}
-
-__device__ __forceinline__ f32x2 pair_dist_direct(const float4 &A, f32x2 Z, const QueryConst &q) {
-    // pytorch3d: d = fma(dz,dz, fma(dy,dy, dx*dx)); (r-q)^2 == (q-r)^2 bit for bit
-    const f32x2 dx = add2(pack2(A.x, A.y), q.a0), dy = add2(pack2(A.z, A.w), q.a1), dz = add2(Z, q.a2);
-    f32x2 t = mul2(dx, dx);
-    t = fma2(dy, dy, t);
-    return fma2(dz, dz, t);
-}
-
-// prefilter value of the 4 refs of half a chunk given its HREC records -> min of the four
-template <int FORM>
-__device__ __forceinline__ float half_chunk_min(const float4 (&H)[Lay<FORM>::HREC], const QueryConst &q) {
+__device__ __forceinline__ float half_chunk_umin(const float4 (&H)[4], f32x2 b0, f32x2 b1, f32x2 b2) {
     float d0, d1, d2, d3;
-    if (FORM == B200PC_FORM_DIRECT) {
-        unpack2(pair_dist_direct(H[0], pack2(H[2].x, H[2].y), q), d0, d1);
-        unpack2(pair_dist_direct(H[1], pack2(H[2].z, H[2].w), q), d2, d3);
-    } else {
-        unpack2(pair_prefilter<FORM>(H[0], H[Lay<FORM>::HREC - 3], q), d0, d1);
-        unpack2(pair_prefilter<FORM>(H[Lay<FORM>::HREC - 2], H[Lay<FORM>::HREC - 1], q), d2, d3);
-    }
-    return fminf(min3(d0, d1, d2), d3);
+    unpack2(pair_u(H[0], H[1], b0, b1, b2), d0, d1);
+    unpack2(pair_u(H[2], H[3], b0, b1, b2), d2, d3);
+    return fminf(min3(d0, d1, d2), d3);      // FMNMX returns the non-NaN operand: a NaN (padding) never wins
 }
-
-template <int FORM>
-__device__ __forceinline__ float chunk_min(const float4 (&R)[Lay<FORM>::REC], const QueryConst &q) {
-    constexpr int H = Lay<FORM>::HREC;
-    float4 lo[H], hi[H];
+__device__ __forceinline__ float chunk_umin(const float4 (&R)[REC], f32x2 b0, f32x2 b1, f32x2 b2) {
+    float d[8];
 #pragma unroll
-    for (int i = 0; i < H; ++i) { lo[i] = R[i]; hi[i] = R[H + i]; }
-    return fminf(half_chunk_min<FORM>(lo, q), half_chunk_min<FORM>(hi, q));
+    for (int p = 0; p < 4; ++p) unpack2(pair_u(R[2 * p], R[2 * p + 1], b0, b1, b2), d[2 * p], d[2 * p + 1]);
+    return min3(min3(d[0], d[1], d[2]), min3(d[3], d[4], d[5]), fminf(d[6], d[7]));
 }
 
-// exact distances of logical pair p (refs 2p, 2p+1) of a chunk whose records start at `cb` (drain path)
+// Threshold of the filter.  Claim: for every ref,  dist_ref(q, r) < tau  (or <=)  implies  u < thr  (or <=), where
+// dist_ref is the reference's rounded distance in any of the three forms and u is pair_u's value on the packed record.
+//   eps = 2^-24, nq = fl|q|^2, w = fl|r|^2, w' = filter_norm(w) <= w (1 - 18.9 eps), a = -2q,
+//   U = x a0 + y a1 + z a2 + w (real arithmetic),  M = |x a0| + |y a1| + |z a2| + w <= 2|q||r| + w <= 1.001 nq + 2.001 w.
+//   * u is a 3-rounding evaluation of U - (w - w'):                                u <= U - (w - w') + 3.01 eps M
+//   * forms 0/1 are 5-rounding evaluations of U + nq:                       |dist_ref - (U + nq)| <= 5.01 eps (M + nq)
+//   * form 2 is a 5-rounding evaluation of |r - q|^2 (positive terms only) and |r - q|^2 differs from U + nq by the
+//     rounding of the two norms:                             |dist_ref - (U + nq)| <= 5.01 eps |tau| + 4.01 eps (nq + w)
+//   so dist_ref < tau  =>  u < (tau - nq) + 5.01 eps |tau| + 8.02 eps M + 5.01 eps nq - (w - w')
+//                            <= (tau - nq) + 5.01 eps |tau| + 13.1 eps nq + (16.1 - 18.9) eps w.
+//   * fl(tau - nq) and the final addition add at most eps (|tau| + nq) each.
+//   Query-side margin needed: 7.1 eps |tau| + 15.2 eps nq; used: 7.5 eps and 18.4 eps, plus an absolute 1e-35 for
+//   products that underflow.  A non-finite margin (inf / NaN coordinates) opens the filter completely -- the drain's
+//   exact test decides, as the reference's own arithmetic would.
+__device__ __forceinline__ float filter_threshold(float tau, float nq) {
+    const float margin = 4.5e-7f * fabsf(tau) + (1.1e-6f * nq + 1e-35f);
+    if (tau == -CUDART_INF_F) return tau;
+    return margin < CUDART_INF_F ? (tau - nq) + margin : CUDART_INF_F;
+}
+
+// exact distances of logical pair p (refs 2p, 2p+1) of chunk `chunk` whose records start at `cb`
 template <int FORM>
 __device__ __forceinline__ f32x2 chunk_pair_dist(const float4 *cb, int chunk, int p, const QueryConst &q) {
-    if (FORM == B200PC_FORM_DIRECT) {
-        const float4 *h = cb + (p >> 1) * 3;
-        const float4 Z = h[2];
-        return pair_dist_direct(h[p & 1], (p & 1) ? pack2(Z.z, Z.w) : pack2(Z.x, Z.y), q);
-    }
     const float4 *pp = cb + 2 * (p ^ (chunk & 3));       // un-swizzle: where pair p of this chunk lives
     return pair_dist<FORM>(pp[0], pp[1], q);
 }
@@ -215,6 +192,7 @@ struct SearchArgs {
     int N, n_pad, S, k;
     float r2;              // ball radius^2 (fp32)
     int debug_nodrain;     // measurement only: start with tau = -inf so nothing ever hits
+    int lane_filter;       // 1: refs in registers, queries broadcast (default); 0: queries in registers, refs broadcast
     int n_split, tiles_per_split;
     int64_t *idx_out;      // [B][S][k]   (n_split == 1)
     float *dist_out;       // [B][S][k] or null
@@ -266,25 +244,22 @@ __device__ __forceinline__ void heap_sift_root(uint32_t hb, uint32_t SB, uint32_
     sts_u64(hb + pos, nk);
 }
 
-constexpr int CAND_CAP = 32;  // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a sub-tile
+constexpr int CAND_CAP = 16;  // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a drain pass
 
 template <int FORM>
 __device__ __forceinline__ float tile_dist(const float4 *tp, int off, const QueryConst &q) {
     float lo, hi;
     const int chunk = off >> 3;
-    unpack2(chunk_pair_dist<FORM>(tp + chunk * Lay<FORM>::REC, chunk, (off >> 1) & 3, q), lo, hi);   // same packed arithmetic as the hot loop
+    unpack2(chunk_pair_dist<FORM>(tp + chunk * REC, chunk, (off >> 1) & 3, q), lo, hi);   // same packed arithmetic for all refs
     return (off & 1) ? hi : lo;
 }
 
 constexpr int MAX_WARPS = 16;
+constexpr int MAX_WARPS_Q1 = 14;   // Q=1 kernels are compiled for two resident CTAs of 14 warps (<= 72 registers)
 
-// Every warp is a consumer; there is no dedicated producer warp.  The ring is refilled by whichever
-// warp happens to release a stage LAST: after arriving on the stage's "empty" barrier each warp
-// probes it once (no spinning) and, if the phase is complete, claims the refill with a shared-memory
-// compare-and-swap and issues the bulk copy.  blockDim.x = warps * 32 is a RUNTIME value so that the
-// planner can size the grid as whole waves of resident CTAs.
+// blockDim.x = warps * 32 is a RUNTIME value so that the planner can size the grid as whole waves of resident CTAs.
 template <int FORM, int MODE, int Q>
-__global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs P) {
+__global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q == 1 ? 2 : 1) search_kernel(const SearchArgs P) {
     const int NCW = (int)(blockDim.x >> 5);       // warps
     const int NCT = NCW * 32;                     // threads
     const int QPB = NCT * Q;                      // queries per block
@@ -293,8 +268,10 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
     const float4 *tiles = reinterpret_cast<const float4 *>(smem);
     const uint32_t bar_base = smem_u32(smem + STAGES * TILE_BYTES);   // full[s] at +8s, empty[s] at +8(STAGES+s)
     int *issued = reinterpret_cast<int *>(smem + STAGES * TILE_BYTES + 8 * 2 * STAGES);   // tiles issued so far
-    // top-k: heap [k][QPB] u64, then candidate buffer [CAND_CAP][QPB] u16.   ball: list [k][QPB] u32
-    unsigned long long *heap_all = reinterpret_cast<unsigned long long *>(smem + STAGES * TILE_BYTES + BAR_BYTES);
+    // query records [QPB] float4 {-2qx, -2qy, -2qz, filter threshold} (read by the lane filter), then
+    // top-k: heap [k+1][QPB] u64 and candidate buffer [CAND_CAP][QPB] u16.   ball: list [k][QPB] u32
+    float4 *qrec = reinterpret_cast<float4 *>(smem + STAGES * TILE_BYTES + BAR_BYTES);
+    unsigned long long *heap_all = reinterpret_cast<unsigned long long *>(qrec + QPB);
     unsigned short *cand_all = reinterpret_cast<unsigned short *>(heap_all + (size_t)(P.k + 1) * QPB);
     int *list_all = reinterpret_cast<int *>(heap_all);
 
@@ -304,8 +281,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
     const int tile1 = min(tile0 + P.tiles_per_split, P.n_pad / TILE);
     const int ntiles = tile1 - tile0;
     const int k = P.k;
-    constexpr int REC = Lay<FORM>::REC, HREC = Lay<FORM>::HREC, TCOPY = Lay<FORM>::TILE_COPY;
-    const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * (P.n_pad / TILE) + (size_t)tile0) * TCOPY;
+    const char *src = reinterpret_cast<const char *>(P.packed) + ((size_t)b * P.n_pad + (size_t)tile0 * TILE) * 16;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -316,15 +292,16 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
         mbar_fence_init();
         const int pre = ntiles < STAGES ? ntiles : STAGES;
         for (int t = 0; t < pre; ++t) {
-            mbar_expect_tx(bar_base + 8 * t, TCOPY);
-            bulk_g2s(smem_u32(smem + t * TILE_BYTES), src + (size_t)t * TCOPY, TCOPY, bar_base + 8 * t);
+            mbar_expect_tx(bar_base + 8 * t, TILE_BYTES);
+            bulk_g2s(smem_u32(smem + t * TILE_BYTES), src + (size_t)t * TILE_BYTES, TILE_BYTES, bar_base + 8 * t);
         }
         *issued = pre;
     }
     __syncthreads();
 
     const int ct = threadIdx.x;  // 0 .. NCT-1
-    QueryConst qc[Q];
+    // Per-query state that stays in registers across the filter: tau (exact threshold) and the ball count.  Everything
+    // else about a query is rebuilt from its 16-byte shared-memory record at the start of a drain.
     float tau[Q];
     int cnt[Q];
 #pragma unroll
@@ -335,7 +312,6 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
             const float *qp = P.qry + ((size_t)b * P.S + qi) * 3;
             x = qp[0]; y = qp[1]; z = qp[2];
         }
-        qc[j] = make_query<FORM>(x, y, z);
         cnt[j] = 0;
         if (MODE == MODE_TOPK) {
             tau[j] = P.debug_nodrain ? -CUDART_INF_F : CUDART_INF_F;
@@ -344,6 +320,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
         } else {
             tau[j] = P.r2;
         }
+        qrec[j * NCT + ct] = make_float4(-2.0f * x, -2.0f * y, -2.0f * z, filter_threshold(tau[j], torch_sq_norm(x, y, z)));
     }
 
     for (int t = 0; t < ntiles; ++t) {
@@ -352,98 +329,100 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
         const float4 *tp = tiles + (size_t)s * TILE;
         const int tile_ref0 = (tile0 + t) * TILE;
 
-        int c = 0;
-        while (c < CHUNKS_PER_TILE) {
-            // warm-up (first tile of the split only): drain after 2,2,4,8,16,32 chunks so that tau
-            // tightens quickly; afterwards once per tile (64 chunks, two 32-bit hit masks).
-            int nch = CHUNKS_PER_TILE;
-            if (t == 0) nch = c < 2 ? 2 : (c < 32 ? c : 32);
-            if (nch > CHUNKS_PER_TILE - c) nch = CHUNKS_PER_TILE - c;
-
-            // ---- hot loop: distance + half a min per pair, one compare per chunk, no branches ----
+        // ---- filter A (broadcast): queries in registers, every lane walks the same nch <= 32 chunks from c ----
+        auto filter_bcast = [&](const int c, const int nch, uint32_t (&mask)[Q][2]) {
+            f32x2 b0[Q], b1[Q], b2[Q];
             float thr[Q];
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
-                float lo, hi;
-                unpack2(qc[j].a3, lo, hi);
-                thr[j] = prefilter_threshold<FORM>(tau[j], lo);
+                const float4 qv = qrec[j * NCT + ct];
+                b0[j] = splat2(qv.x); b1[j] = splat2(qv.y); b2[j] = splat2(qv.z); thr[j] = qv.w;
+                mask[j][0] = 0u; mask[j][1] = 0u;
             }
-            uint32_t mask[Q][2];
+            // register double buffer: half a chunk is requested ahead of its use and a warp-level memory barrier
+            // pins those loads above the math of the current group (ptxas would sink every LDS next to its use).
+            const float4 *cp = tp + c * REC;
+            float4 H[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) H[p] = cp[p];
+            uint32_t bit = 1u;
+            for (int cc = 0; cc < nch; ++cc, bit <<= 1) {
+                float4 N1[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) N1[p] = cp[4 + p];
+                __syncwarp();
+                float ma[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) ma[j] = half_chunk_umin(H, b0[j], b1[j], b2[j]);
+                cp += REC;       // one chunk past the tile end is still inside the ring / barrier block: harmless
+                float4 N2[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) N2[p] = cp[p];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    const float m = fminf(ma[j], half_chunk_umin(N1, b0[j], b1[j], b2[j]));
+                    const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= thr[j]);
+                    if (hit) mask[j][0] |= bit;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) H[p] = N2[p];
+            }
+        };
+
+        // ---- filter B (lanes): lane l keeps chunk c0+32h+l (8 refs) in registers and the warp's 32*Q queries are
+        // broadcast one at a time from their shared-memory records; the ballot of query i is exactly the 32-chunk
+        // hit mask that lane i needs for its drain.
+        auto filter_lanes = [&](const int c0, uint32_t (&mask)[Q][2]) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) { mask[j][0] = 0u; mask[j][1] = 0u; }
-            const float4 *cp = tp + c * REC;
-            // register double buffer: records are requested ahead of their use and a warp-level memory barrier
-            // pins those loads above the math of the current group, so the shared-memory latency is covered
-            // (without it ptxas sinks every LDS next to its first use).  Q=2: a whole chunk ahead; Q=1: half a
-            // chunk ahead, which keeps the kernel under 72 registers so that twice as many warps stay resident.
-            if (Q >= 2) {
+            __syncwarp();                                     // the owners' threshold updates are visible
+#pragma unroll 1
+            for (int h = 0; c0 + 32 * h < CHUNKS_PER_TILE; ++h) {
                 float4 R[REC];
+                {
+                    // lane-distinct 16-byte loads: rotate the pair slot by the lane so that a quarter warp covers
+                    // four different 32-byte slots (2-way instead of 32-way conflicts).  The pair ORDER inside a
+                    // chunk does not matter to a min; the two records of a pair stay together.
+                    const float4 *cb = tp + (c0 + 32 * h + lane) * REC;
+                    const int rot = (lane & 3) << 1;
 #pragma unroll
-                for (int p = 0; p < REC; ++p) R[p] = cp[p];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
-                    uint32_t bit = 1u;
-                    for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
-                        cp += REC;     // one chunk past the tile end is still inside the ring / barrier block: harmless
-                        float4 Nx[REC];
-#pragma unroll
-                        for (int p = 0; p < REC; ++p) Nx[p] = cp[p];
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < Q; ++j) {
-                            const float m = chunk_min<FORM>(R, qc[j]);
-                            const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
-                            if (hit) mask[j][half] |= bit;
-                        }
-#pragma unroll
-                        for (int p = 0; p < REC; ++p) R[p] = Nx[p];
-                    }
+                    for (int p = 0; p < REC; ++p) R[p] = cb[p ^ rot];
                 }
-            } else {
-                float4 H[HREC];
 #pragma unroll
-                for (int p = 0; p < HREC; ++p) H[p] = cp[p];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int n_here = half == 0 ? (nch < 32 ? nch : 32) : nch - 32;
-                    uint32_t bit = 1u;
-                    for (int cc = 0; cc < n_here; ++cc, bit <<= 1) {
-                        float4 N1[HREC];
-#pragma unroll
-                        for (int p = 0; p < HREC; ++p) N1[p] = cp[HREC + p];
-                        __syncwarp();
-                        float ma[Q];
-#pragma unroll
-                        for (int j = 0; j < Q; ++j) ma[j] = half_chunk_min<FORM>(H, qc[j]);
-                        cp += REC;
-                        float4 N2[HREC];
-#pragma unroll
-                        for (int p = 0; p < HREC; ++p) N2[p] = cp[p];
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < Q; ++j) {
-                            const float m = fminf(ma[j], half_chunk_min<FORM>(N1, qc[j]));
-                            const bool hit = MODE == MODE_TOPK ? (m < thr[j]) : (m <= tau[j]);
-                            if (hit) mask[j][half] |= bit;
-                        }
-#pragma unroll
-                        for (int p = 0; p < HREC; ++p) H[p] = N2[p];
+                for (int j = 0; j < Q; ++j) {
+                    const int s0 = j * NCT + (ct & ~31);
+                    uint32_t mine = 0u;
+#pragma unroll 4
+                    for (int l = 0; l < 32; ++l) {
+                        const float4 qv = qrec[s0 + l];
+                        const float m = chunk_umin(R, splat2(qv.x), splat2(qv.y), splat2(qv.z));
+                        const bool hit = MODE == MODE_TOPK ? (m < qv.w) : (m <= qv.w);
+                        const uint32_t bal = __ballot_sync(FULL, hit);
+                        if (lane == l) mine = bal;
                     }
+                    if (h == 0) mask[j][0] = mine; else mask[j][1] = mine;
                 }
             }
+        };
 
-            // ---- drain, warp-synchronous so that the lanes' slow work overlaps instead of serialising ----
+        // ---- drain, warp-synchronous so that the lanes' slow work overlaps instead of serialising ----
+        auto drain = [&](const int c, uint32_t (&mask)[Q][2]) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
                 uint32_t m0 = mask[j][0], m1 = mask[j][1];
                 const int slot = j * NCT + ct;
+                const float4 qv = qrec[slot];
+                // x = -0.5 * (-2x) exactly, so this is the same QueryConst the coordinates would give
+                const QueryConst qcj = make_query<FORM>(-0.5f * qv.x, -0.5f * qv.y, -0.5f * qv.z);
                 if (MODE == MODE_TOPK) {
                     const uint32_t hb = smem_u32(heap_all + slot), SB = (uint32_t)QPB * 8u;
                     unsigned short *cand = cand_all + slot;
+                    const f32x2 b0 = splat2(qv.x), b1 = splat2(qv.y), b2 = splat2(qv.z);
+                    const float thr = qv.w;
                     while (__any_sync(FULL, (m0 | m1) != 0u)) {
-                        // phase 1: every lane revisits its r-th hit chunk; the chunk's candidates (d < stale tau)
-                        // are only recorded, as ONE entry (chunk << 8 | 8-bit mask), at most CAND_CAP per pass.
+                        // phase 1: every lane revisits its r-th hit chunk; the refs that pass the filter test on their
+                        // own are only recorded, as ONE entry (chunk << 8 | 8-bit mask), at most CAND_CAP per pass.
                         int nc = 0;
                         while (__any_sync(FULL, (m0 | m1) != 0u && nc < CAND_CAP)) {
                             if ((m0 | m1) != 0u && nc < CAND_CAP) {
@@ -451,12 +430,17 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                                 if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
                                 else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
                                 const float4 *dp = tp + (c + cc) * REC;
-                                float d[8];
+                                // logical pair p lives in pair slot p ^ (chunk & 3): lanes on different chunks spread over the banks
+                                const float4 *dq = dp + 2 * ((c + cc) & 3);
+                                float u[8];
 #pragma unroll
-                                for (int p = 0; p < 4; ++p) unpack2(chunk_pair_dist<FORM>(dp, c + cc, p, qc[j]), d[2 * p], d[2 * p + 1]);
+                                for (int p = 0; p < 4; ++p) {
+                                    const float4 *pp = reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(dq) ^ (uintptr_t)(p * 32));
+                                    unpack2(pair_u(pp[0], pp[1], b0, b1, b2), u[2 * p], u[2 * p + 1]);
+                                }
                                 uint32_t cm = 0u;
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) cm |= (d[i] < tau[j]) ? (1u << i) : 0u;
+                                for (int i = 0; i < 8; ++i) cm |= (u[i] < thr) ? (1u << i) : 0u;
                                 if (cm != 0u) { cand[nc * QPB] = (unsigned short)((cc << 8) | cm); ++nc; }
                             }
                         }
@@ -474,13 +458,19 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                             if (cur != 0u) {
                                 const int off = base + __ffs(cur) - 1;
                                 cur &= cur - 1;
-                                const float d = tile_dist<FORM>(tp, off, qc[j]);
+                                const float d = tile_dist<FORM>(tp, off, qcj);
                                 if (d < tau[j]) {
                                     heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | (uint32_t)(tile_ref0 + off));
                                     tau[j] = key_to_float((uint32_t)(lds_u64(hb) >> 32));
                                 }
                             }
                         }
+                    }
+                    // publish the tightened threshold to the filters
+                    {
+                        float nq, dummy;
+                        unpack2(qcj.a3, nq, dummy);
+                        reinterpret_cast<float *>(qrec + slot)[3] = filter_threshold(tau[j], nq);
                     }
                 } else {
                     int *list = list_all + slot;
@@ -493,15 +483,36 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
                             const float4 *dp = tp + (c + cc) * REC;
                             float d[8];
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) unpack2(chunk_pair_dist<FORM>(dp, c + cc, p, qc[j]), d[2 * p], d[2 * p + 1]);
+                            for (int p = 0; p < 4; ++p) unpack2(chunk_pair_dist<FORM>(dp, c + cc, p, qcj), d[2 * p], d[2 * p + 1]);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 if (d[i] <= tau[j] && cnt[j] < k) { list[cnt[j] * QPB] = tile_ref0 + off0 + i; ++cnt[j]; }
-                            if (cnt[j] == k) { tau[j] = -CUDART_INF_F; m0 = 0u; m1 = 0u; }   // this query is complete
+                            if (cnt[j] == k) {   // this query is complete: nothing can hit any more
+                                tau[j] = -CUDART_INF_F; m0 = 0u; m1 = 0u;
+                                reinterpret_cast<float *>(qrec + slot)[3] = -CUDART_INF_F;
+                            }
                         }
                     }
                 }
             }
+        };
+
+        // Schedule.  First tile of a split (top-k only): the broadcast filter with a drain after 2,2,4,8,16 chunks so
+        // that tau tightens quickly, then the lane filter on the second half.  Every other tile: the lane filter on
+        // both halves (two 32-bit hit masks per query) and ONE drain.
+        uint32_t mask[Q][2];
+        const bool warm = MODE == MODE_TOPK && t == 0;
+        int c = 0;
+        while (c < CHUNKS_PER_TILE) {
+            int nch = CHUNKS_PER_TILE - c;
+            if (P.lane_filter && !(warm && c < 32)) {
+                filter_lanes(c, mask);
+            } else {
+                nch = warm ? (c < 2 ? 2 : c) : 32;
+                if (nch > 32) nch = 32;
+                filter_bcast(c, nch, mask);
+            }
+            drain(c, mask);
             c += nch;
         }
 
@@ -513,8 +524,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) search_kernel(const SearchArgs
             const int nxt = t + STAGES;                 // the tile that will reuse this stage
             if (nxt < ntiles && mbar_test(ebar, (t / STAGES) & 1)) {
                 if (atomicCAS(issued, nxt, nxt + 1) == nxt) {
-                    mbar_expect_tx(bar_base + 8 * s, TCOPY);
-                    bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)nxt * TCOPY, TCOPY, bar_base + 8 * s);
+                    mbar_expect_tx(bar_base + 8 * s, TILE_BYTES);
+                    bulk_g2s(smem_u32(smem + s * TILE_BYTES), src + (size_t)nxt * TILE_BYTES, TILE_BYTES, bar_base + 8 * s);
                 }
             }
         }
@@ -614,8 +625,8 @@ __global__ void merge_ball_kernel(const int *__restrict__ part_i, const int *__r
 // ---------------------------------------------------------------------------------------------
 // 5. planning + launch
 // ---------------------------------------------------------------------------------------------
-// per-query shared-memory bytes.  top-k: u64 heap [k] + u16 candidate buffer [CAND_CAP];  ball: u32 list [nsample]
-static size_t query_bytes(int k, int mode) { return mode == MODE_TOPK ? (size_t)(k + 1) * 8 + (size_t)CAND_CAP * 2 : (size_t)k * 4; }
+// per-query shared-memory bytes: 16-byte query record, then  top-k: u64 heap [k] + u16 candidate buffer [CAND_CAP];  ball: u32 list [nsample]
+static size_t query_bytes(int k, int mode) { return 16 + (mode == MODE_TOPK ? (size_t)(k + 1) * 8 + (size_t)CAND_CAP * 2 : (size_t)k * 4); }
 static const size_t kMaxSmem = 227 * 1024;
 static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 
@@ -644,7 +655,7 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
             const size_t budget = kMaxSmem / c - 1024;          // ~1 KB per resident CTA is reserved by the system
             if (budget <= kFixedSmem + 32 * q * qb) continue;
             int wmax = (int)((budget - kFixedSmem) / (32 * q * qb));
-            if (wmax > MAX_WARPS) wmax = MAX_WARPS;
+            if (wmax > (q == 1 ? MAX_WARPS_Q1 : MAX_WARPS)) wmax = q == 1 ? MAX_WARPS_Q1 : MAX_WARPS;
             const long slots = (long)sms * c;
             for (int split = 1; split <= MAX_SPLIT && split <= pl->n_tiles; split = split < 4 ? split + 1 : split * 2) {
                 if (force_split && split != (force_split > pl->n_tiles ? pl->n_tiles : force_split)) continue;
@@ -732,13 +743,15 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     float4 *packed = reinterpret_cast<float4 *>(w);
     {
         dim3 grid((pl.n_pad / 2 + 255) / 256, B);
-        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, form, packed);
+        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, packed);
         B200PC_LAUNCH_CHECK();
     }
     SearchArgs a;
     a.packed = packed; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
     a.debug_nodrain = getenv("B200PC_DEBUG_NODRAIN") != nullptr;
+    a.lane_filter = 1;
+    if (const char *e = getenv("B200PC_FILTER")) a.lane_filter = atoi(e) != 0;   // A/B measurement only
     a.idx_out = idx; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;
