@@ -254,7 +254,20 @@ __device__ __forceinline__ float tile_dist(const float4 *tp, int off, const Quer
     return (off & 1) ? hi : lo;
 }
 
+// 32 x 32 bit-matrix transpose across a warp: on return, bit i of lane l's word is bit l of lane i's input word
+// (five butterfly stages; replaces 32 x (ballot + compare + select)).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) == 0 ? ((x & m) | ((other << s) & ~m)) : ((x & ~m) | ((other >> s) & m));
+    }
+    return x;
+}
+
 constexpr int MAX_WARPS = 16;
+constexpr int FILTER_UNROLL = 8;   // queries of the lane filter in flight per warp
 constexpr int MAX_WARPS_Q1 = 14;   // Q=1 kernels are compiled for two resident CTAs of 14 warps (<= 72 registers)
 
 // blockDim.x = warps * 32 is a RUNTIME value so that the planner can size the grid as whole waves of resident CTAs.
@@ -392,15 +405,15 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
                     const int s0 = j * NCT + (ct & ~31);
-                    uint32_t mine = 0u;
-#pragma unroll 4
+                    uint32_t mine = 0u;                       // bit l: my chunk holds a candidate of the warp's l-th query
+#pragma unroll FILTER_UNROLL
                     for (int l = 0; l < 32; ++l) {
                         const float4 qv = qrec[s0 + l];
                         const float m = chunk_umin(R, splat2(qv.x), splat2(qv.y), splat2(qv.z));
                         const bool hit = MODE == MODE_TOPK ? (m < qv.w) : (m <= qv.w);
-                        const uint32_t bal = __ballot_sync(FULL, hit);
-                        if (lane == l) mine = bal;
+                        if (hit) mine |= 1u << l;
                     }
+                    mine = warp_transpose32(mine, lane);      // bit i: chunk c0+32h+i holds a candidate of MY query
                     if (h == 0) mask[j][0] = mine; else mask[j][1] = mine;
                 }
             }
