@@ -246,12 +246,22 @@ __device__ __forceinline__ void heap_sift_root(uint32_t hb, uint32_t SB, uint32_
 
 constexpr int CAND_CAP = 16;  // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a drain pass
 
+// Exact distance of ONE ref of the tile (ref number `off`), scalar: the same IEEE operations in the same order as
+// pair_dist (explicit .rn intrinsics, so nothing is contracted), a third of its instructions.  (ax, ay, az) is -2q for
+// the expanded forms and -q for the direct form; nq = fl|q|^2.
 template <int FORM>
-__device__ __forceinline__ float tile_dist(const float4 *tp, int off, const QueryConst &q) {
-    float lo, hi;
+__device__ __forceinline__ float ref_dist(const float4 *tp, int off, float ax, float ay, float az, float nq) {
     const int chunk = off >> 3;
-    unpack2(chunk_pair_dist<FORM>(tp + chunk * REC, chunk, (off >> 1) & 3, q), lo, hi);   // same packed arithmetic for all refs
-    return (off & 1) ? hi : lo;
+    const float *rec = reinterpret_cast<const float *>(tp + chunk * REC + 2 * (((off >> 1) ^ chunk) & 3)) + (off & 1);
+    const float x = rec[0], y = rec[2], z = rec[4];
+    if (FORM == B200PC_FORM_DIRECT) {
+        const float dx = __fadd_rn(x, ax), dy = __fadd_rn(y, ay), dz = __fadd_rn(z, az);
+        return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    }
+    const float t = __fmaf_rn(z, az, __fmaf_rn(y, ay, __fmul_rn(x, ax)));
+    const float w = torch_sq_norm(x, y, z);
+    if (FORM == B200PC_FORM_REF_NORM_FIRST) return __fadd_rn(__fadd_rn(t, w), nq);
+    return __fadd_rn(__fadd_rn(t, nq), w);
 }
 
 // 32 x 32 bit-matrix transpose across a warp: on return, bit i of lane l's word is bit l of lane i's input word
@@ -426,9 +436,11 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                 uint32_t m0 = mask[j][0], m1 = mask[j][1];
                 const int slot = j * NCT + ct;
                 const float4 qv = qrec[slot];
-                // x = -0.5 * (-2x) exactly, so this is the same QueryConst the coordinates would give
-                const QueryConst qcj = make_query<FORM>(-0.5f * qv.x, -0.5f * qv.y, -0.5f * qv.z);
+                // x = -0.5 * (-2x) exactly, so these are the constants the coordinates themselves would give
+                const float nq = torch_sq_norm(0.5f * qv.x, 0.5f * qv.y, 0.5f * qv.z);
                 if (MODE == MODE_TOPK) {
+                    const float ex = FORM == B200PC_FORM_DIRECT ? 0.5f * qv.x : qv.x, ey = FORM == B200PC_FORM_DIRECT ? 0.5f * qv.y : qv.y,
+                                ez = FORM == B200PC_FORM_DIRECT ? 0.5f * qv.z : qv.z;
                     const uint32_t hb = smem_u32(heap_all + slot), SB = (uint32_t)QPB * 8u;
                     unsigned short *cand = cand_all + slot;
                     const f32x2 b0 = splat2(qv.x), b1 = splat2(qv.y), b2 = splat2(qv.z);
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                             if (cur != 0u) {
                                 const int off = base + __ffs(cur) - 1;
                                 cur &= cur - 1;
-                                const float d = tile_dist<FORM>(tp, off, qcj);
+                                const float d = ref_dist<FORM>(tp, off, ex, ey, ez, nq);
                                 if (d < tau[j]) {
                                     heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | (uint32_t)(tile_ref0 + off));
                                     tau[j] = key_to_float((uint32_t)(lds_u64(hb) >> 32));
@@ -480,12 +492,9 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                         }
                     }
                     // publish the tightened threshold to the filters
-                    {
-                        float nq, dummy;
-                        unpack2(qcj.a3, nq, dummy);
-                        reinterpret_cast<float *>(qrec + slot)[3] = filter_threshold(tau[j], nq);
-                    }
+                    reinterpret_cast<float *>(qrec + slot)[3] = filter_threshold(tau[j], nq);
                 } else {
+                    const QueryConst qcj = make_query<FORM>(-0.5f * qv.x, -0.5f * qv.y, -0.5f * qv.z);
                     int *list = list_all + slot;
                     while (__any_sync(FULL, (m0 | m1) != 0u)) {
                         if ((m0 | m1) != 0u) {
@@ -646,7 +655,7 @@ static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 // Choose {queries per thread, consumer warps, ref split} so that the grid is (close to) a whole
 // number of waves of resident CTAs: CTA count = B * ceil(S / q_per_block) * n_split against
 // slots = SMs * CTAs-per-SM.  Among the candidates the one with the best wave efficiency wins;
-// ties go to more resident warps, then to Q=2 (half the shared-memory loads per pair).
+// ties go to more resident warps.
 bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     const int sms = sm_count();
     const size_t qb = query_bytes(k, mode);
@@ -662,8 +671,11 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     double best_score = -1.0;
     int best_q = 1, best_w = 1, best_split = 1;
     const double lnk = 1.0 + log(fmax(1.0, (double)N / k));
-    for (int q = 2; q >= 1; --q) {
-        if (force_q && q != force_q) continue;
+    for (int q = 1; q <= 2; ++q) {
+        // With the lane filter the queries per thread only matter to the drain, where two queries per lane drain one
+        // after the other with half the resident warps: measured 20-40 % slower on every shape, so Q=2 is kept for
+        // A/B measurements (B200PC_FORCE_Q=2) only.
+        if (force_q ? q != force_q : q != 1) continue;
         for (int c = 1; c <= 8; ++c) {                       // target CTAs per SM
             const size_t budget = kMaxSmem / c - 1024;          // ~1 KB per resident CTA is reserved by the system
             if (budget <= kFixedSmem + 32 * q * qb) continue;
@@ -679,7 +691,7 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
                 if (w < 1) w = 1;
                 if (w > wmax) w = wmax;
                 if (force_w) w = force_w > wmax ? wmax : force_w;
-                // register file: 64K registers per SM, ~125 (Q=2) / <=72 (Q=1) per thread
+                // register file: 64K registers per SM, <= 128 (Q=2) / <= 72 (Q=1) per thread
                 if ((long)w * 32 * c * (q == 2 ? 128 : 72) > 65536) continue;
                 const long items = (long)B * (((long)S + 32L * q * w - 1) / (32L * q * w));
                 const int tps = (pl->n_tiles + split - 1) / split;
@@ -694,7 +706,7 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
                 // a split repeats the warm-up of the k-best list in every ref range: ~k(1+ln(n/k)) candidates each
                 const double drain = real_split * (1.0 + log(fmax(1.0, (double)N / real_split / k))) / lnk;
                 const double work = 0.5 + 0.5 * drain + (real_split > 1 ? 0.05 : 0.0);
-                const double score = wave_eff * pad_eff * occ / work + 1e-3 * (q == 2) + 1e-5 * resident;
+                const double score = wave_eff * pad_eff * occ / work + 1e-5 * resident;
                 if (score > best_score) { best_score = score; best_q = q; best_w = w; best_split = real_split; }
             }
         }
