@@ -96,11 +96,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"   // suspend-time hint: park the warp instead of spinning
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
+        "}" ::"r"(bar), "r"(parity), "r"(20000u)
         : "memory");
 }
 // single non-blocking probe: has the phase with this parity completed?

@@ -186,3 +186,45 @@ def test_c2_full_size_properties(cuda_dev):
     np.testing.assert_array_equal(_bits(d[:2, sel]), _bits(od))
     ball = P.query_ball_point(1.0, 32, ref, qry).cpu().numpy()
     np.testing.assert_array_equal(ball[:1, sel], strict.query_ball_point(1.0, 32, a[:1], b[:1, sel]))
+
+
+# ---- the conservative prefilter (search.cu filter_threshold): exactness must not depend on magnitudes ----
+@pytest.mark.parametrize("form", [0, 1, 2])
+@pytest.mark.parametrize("offset,scale", [((1000.0, -2500.0, 300.0), 1.0),     # far from the origin: the filter margin is large
+                                          ((0.0, 0.0, 0.0), 1e-12),            # tiny magnitudes
+                                          ((3.0e5, 1.0e5, -2.0e5), 50.0)])     # expanded form cancels catastrophically
+def test_knn_exact_far_from_origin_and_tiny(cuda_dev, form, offset, scale):
+    # Known limit, not covered here: when the dot products themselves are SUBNORMAL (coordinates below ~1e-19) folding
+    # the reference's "-2 *" into the query, s.(-2d) instead of -2(s.d), rounds at a different bit and the expanded
+    # forms differ from the oracle by 1-3 denormal ulps (measured at scale 1e-20; the direct form stays exact).
+    a, b = synth.batch_pairs(21, 2, 3000)
+    off = np.asarray(offset, np.float32)
+    ref = (a[:, :3000] * np.float32(scale) + off).astype(np.float32)
+    qry = (b[:, :700] * np.float32(scale) + off).astype(np.float32)
+    idx, dist = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), 16, form, want_dist=True)
+    oi, od = strict.knn(ref, qry, 16, form)
+    np.testing.assert_array_equal(_bits(dist.cpu().numpy()), _bits(od))
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+
+
+def test_ball_query_exact_far_from_origin(cuda_dev):
+    a, b = synth.batch_pairs(22, 2, 4096)
+    off = np.asarray((800.0, 1200.0, -50.0), np.float32)
+    ref, qry = (a + off).astype(np.float32), (b[:, :512] + off).astype(np.float32)
+    for r, ns in ((0.7, 16), (2.0, 32)):
+        out = P.query_ball_point(r, ns, _t(ref, cuda_dev), _t(qry, cuda_dev))
+        np.testing.assert_array_equal(out.cpu().numpy(), strict.query_ball_point(r, ns, ref, qry))
+
+
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_broadcast_filter_fallback_matches(cuda_dev, monkeypatch, form):
+    # B200PC_FILTER=0 keeps the queries in registers and broadcasts the refs (the warm-up filter, used for the whole
+    # tile): same results by construction, kept under test because it is the A/B baseline of the lane filter
+    a, b = synth.batch_pairs(23, 1, 5000)
+    ref, qry = a[:, :5000].copy(), b[:, :1500].copy()
+    want = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), 16, form, want_dist=True)
+    monkeypatch.setenv("B200PC_FILTER", "0")
+    got = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), 16, form, want_dist=True)
+    assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])
+    oi, od = strict.knn(ref, qry, 16, form)
+    np.testing.assert_array_equal(got[0].cpu().numpy(), oi)
