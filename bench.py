@@ -409,8 +409,9 @@ def main():
                 "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": achieved / FP32_NOMINAL_TFLOPS,
                 "algorithmic": "8 FLOP per (query, ref) pair x %d pairs per launch" % pairs,
                 "note": "K=3 contraction on FP32 CUDA cores (tensor cores would break the rounding parity); the "
-                        "contract's enum is hbm|tensor, this kernel is neither: ncu shows the shared-memory data pipe at "
-                        "88.8 % of peak (profiles/r01_notes.md), DRAM traffic is 3.7 MB against 17.2 GFLOP"}
+                        "contract's enum is hbm|tensor, this kernel is neither: ncu shows it bound by instruction issue (lane "
+                        "filter 35 %, lock-step heap drain 50 % of 495 M warp instructions, profiles/r01_notes.md), DRAM "
+                        "traffic is 3.7 MB against 17.2 GFLOP"}
 
     # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
     cval, csec, cthreads = cpu_reference_knn(a, b, reps=3)

@@ -2,7 +2,7 @@
 
 The reference's loaders hand the models host tensors (`.cuda(non_blocking=True)` in test.py:56-62 of the
 upstream copy) and read results back with `.cpu()`.  For the index-producing searches the read-back is the
-expensive part (int64 indices: 16.8 MB for C2 against a 0.85 ms kernel), so these helpers split the batch into
+expensive part (int64 indices: 16.8 MB for C2 against a 0.72 ms kernel), so these helpers split the batch into
 chunks and double-buffer: while chunk i's indices travel device->host on one stream, chunk i+1 is searched on
 the other.  Results are identical to the plain calls (every op is independent per batch item).
 """
