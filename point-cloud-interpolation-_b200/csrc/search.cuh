@@ -9,8 +9,8 @@ enum SearchMode { MODE_TOPK = 0, MODE_BALL = 1 };
 // Geometry of one search launch, derived deterministically from the problem size so that the
 // workspace-size query and the launcher always agree.
 struct SearchPlan {
-    int q_per_thread;     // queries held by one consumer thread
-    int consumer_warps;   // consumer warps per CTA (one extra warp is the TMA producer)
+    int q_per_thread;     // queries owned by one thread
+    int consumer_warps;   // warps per CTA (all of them consume tiles; there is no producer warp)
     int q_per_block;      // = q_per_thread * consumer_warps * 32
     int n_pad;            // refs padded to a multiple of the tile
     int n_tiles;
