@@ -2,15 +2,21 @@
 
 The reference's loaders hand the models host tensors (`.cuda(non_blocking=True)` in test.py:56-62 of the
 upstream copy) and read results back with `.cpu()`.  For the index-producing searches the read-back is the
-expensive part (int64 indices: 16.8 MB for C2 against a 0.72 ms kernel), so these helpers split the batch into
+expensive part (int64 indices: 16.8 MB for C2 against a 0.72 ms kernel), so these helpers can split the batch into
 chunks and double-buffer: while chunk i's indices travel device->host on one stream, chunk i+1 is searched on
 the other.  Results are identical to the plain calls (every op is independent per batch item).
+
+A chunk must still fill the GPU, though: the search kernel needs ~131 000 queries (148 SMs x 28 warps x 32) in flight,
+and C2 (8 x 16 384) is exactly one such wave -- measured on B200, C2 end to end: 1 chunk 1.13 ms, 2 chunks 1.39 ms,
+4 chunks 1.58 ms (tools/hostio_chunks.py).  `chunks="auto"` (the default) therefore only splits batches that hold
+several waves.
 """
 import torch
 
 from . import pointnet2_utils as P
 
 _STREAMS = {}
+_WAVE_QUERIES = 148 * 28 * 32      # queries one resident wave of the search kernel holds (B200, 14 warps x 2 CTAs per SM)
 
 
 def _streams(device, n):
@@ -23,6 +29,8 @@ def _streams(device, n):
 def _pipelined(op, host_inputs, host_out, device, chunks):
     device = torch.device(device)
     B = host_inputs[0].shape[0]
+    if chunks == "auto":
+        chunks = (B * host_inputs[-1].shape[1]) // _WAVE_QUERIES      # host_inputs[-1] = the queries [B,S,3]
     chunks = max(1, min(int(chunks), B))
     bounds = [(i * B // chunks, (i + 1) * B // chunks) for i in range(chunks)]
     streams = _streams(device, 2)
@@ -39,7 +47,7 @@ def _pipelined(op, host_inputs, host_out, device, chunks):
     return host_out
 
 
-def knn_point_host(nsample, xyz, new_xyz, out=None, device="cuda", chunks=2):
+def knn_point_host(nsample, xyz, new_xyz, out=None, device="cuda", chunks="auto"):
     """knn_point on pinned HOST tensors xyz [B,N,3], new_xyz [B,S,3] -> pinned host int64 [B,S,nsample].
     The copy into `out` is asynchronous: synchronise the device's current stream before reading it."""
     if out is None:
@@ -47,7 +55,7 @@ def knn_point_host(nsample, xyz, new_xyz, out=None, device="cuda", chunks=2):
     return _pipelined(lambda r, q: P.knn_point(nsample, r, q), [xyz, new_xyz], out, device, chunks)
 
 
-def query_ball_point_host(radius, nsample, xyz, new_xyz, out=None, device="cuda", chunks=2):
+def query_ball_point_host(radius, nsample, xyz, new_xyz, out=None, device="cuda", chunks="auto"):
     if out is None:
         out = torch.empty(xyz.shape[0], new_xyz.shape[1], nsample, dtype=torch.int64).pin_memory()
     return _pipelined(lambda r, q: P.query_ball_point(radius, nsample, r, q), [xyz, new_xyz], out, device, chunks)

@@ -89,7 +89,7 @@ def test_hostio_pipelined_knn_equals_plain(cuda_dev):
     from b200pc import hostio
     a, b = synth.batch_pairs(330, 5, 3000)
     h_ref = torch.from_numpy(a).pin_memory(); h_qry = torch.from_numpy(b[:, :1111].copy()).pin_memory()
-    for chunks in (1, 2, 3):
+    for chunks in ("auto", 1, 2, 3):
         out = hostio.knn_point_host(16, h_ref, h_qry, device=cuda_dev, chunks=chunks)
         ball = hostio.query_ball_point_host(1.0, 8, h_ref, h_qry, device=cuda_dev, chunks=chunks)
         torch.cuda.synchronize()
