@@ -108,6 +108,22 @@ int b200pc_gather(const float *points, const int64_t *idx, int B, int N, int C, 
 int b200pc_gather_bwd(const float *gout, const int64_t *idx, int B, int N, int C, int64_t R, float *gpoints,
                       b200pc_stream_t stream);
 
+/* ---- f1: fused grouping  Utils/Layers.py:57-66 (Group.forward tail), ----
+ *      Utils/Pointnet2Utils.py:243-253 (PointNetSetAbstractionMsg.forward grouping)            */
+/* xyz [B,N,3], new_xyz [B,S,3], feat [B,N,D] (NULL when D == 0), idx [B,S,K] from knn / ball query
+ * (negative indices wrap once and out-of-range rows read as zeros, like b200pc_gather).  out [B,3+D,K,S] -- the Conv2d input the
+ * reference builds with two index_points, a subtraction, a cat and a permute+contiguous:
+ *   xyz_first != 0 (Layers.py Group):   out[b,c,k,s]   = xyz[b,idx,c] - new_xyz[b,s,c]  (c < 3)
+ *                                       out[b,3+d,k,s] = feat[b,idx,d]
+ *   xyz_first == 0 (SA-MSG):            features in channels [0,D), relative xyz in [D,D+3).
+ * Bit-identical to the reference (data movement + one fp32 subtraction).                     */
+int b200pc_group_points(const float *xyz, const float *new_xyz, const float *feat, const int64_t *idx, int B, int N,
+                        int S, int K, int D, int xyz_first, float *out, b200pc_stream_t stream);
+/* grad_feat [B,N,D] must be zero-filled by the caller:
+ * grad_feat[b, idx[b,s,k], d] += grad_out[b, (xyz_first ? 3 : 0) + d, k, s]                  */
+int b200pc_group_points_bwd(const float *grad_out, const int64_t *idx, int B, int N, int S, int K, int D,
+                            int xyz_first, float *grad_feat, b200pc_stream_t stream);
+
 /* ---- a9: chamfer_loss  Utils/Utils.py:39-48 -> pytorch3d.loss.chamfer_distance defaults --- */
 /* x [B,N,3], y [B,M,3].  Outputs: per-point nearest squared distance and index in both
  * directions (dx,ix: [B,N]; dy,iy: [B,M]) and the scalar loss[1] =

@@ -123,6 +123,22 @@ def index_points(points, idx):
     return out
 
 
+def group_points(xyz, new_xyz, feat, idx, xyz_first=True):
+    """The grouping tail the fused kernel replaces, restated step by step in numpy (test infrastructure):
+      Utils/Layers.py:57-66      grouped = index_points(points, ind) - new_points.view(B,S,1,C)
+                                 cat([grouped, index_points(features, ind)], -1).permute(0,3,2,1)   (xyz_first)
+      Utils/Pointnet2Utils.py:243-253   cat([index_points(points, idx), grouped_xyz], -1).permute(0,3,2,1)
+    xyz [B,N,3], new_xyz [B,S,3], feat [B,N,D] or None, idx [B,S,K] -> [B,3+D,K,S] float32."""
+    xyz = np.ascontiguousarray(xyz, np.float32); new_xyz = np.ascontiguousarray(new_xyz, np.float32)
+    B, S = new_xyz.shape[0], new_xyz.shape[1]
+    rel = (index_points(xyz, idx) - new_xyz.reshape(B, S, 1, 3)).astype(np.float32)         # one fp32 subtraction
+    parts = [rel]
+    if feat is not None and feat.shape[2] > 0:
+        g = index_points(feat, idx)
+        parts = [rel, g] if xyz_first else [g, rel]
+    return np.ascontiguousarray(np.concatenate(parts, axis=-1).transpose(0, 3, 2, 1))
+
+
 def three_weights(dist, variant):
     dist, pd = _f(dist)
     w = np.empty_like(dist)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "b200pc_fps": (_i, [_p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "b200pc_gather": (_i, [_p, _p, _i, _i, _i, _l, _p, _p, _p]),
     "b200pc_gather_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p, _p]),
+    "b200pc_group_points": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "b200pc_group_points_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "b200pc_chamfer_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
     "b200pc_chamfer_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "b200pc_fma_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), _p]),

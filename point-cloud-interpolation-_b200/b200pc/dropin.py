@@ -67,6 +67,8 @@ def _group_forward(self, points, new_points, features):
         ind = P.knn_point(self.num_samples, pts, qry)
     else:
         ind = P.query_ball_point(self.radius, self.num_samples, pts, qry)
+    if Cx == 3:                                      # the fused kernel: gather, centre, cat and layout change at once
+        return P.group_points(pts, qry, feat, ind)
     rel = P.index_points(pts, ind) - qry.view(B, S, 1, Cx)
     out = torch.cat([rel, P.index_points(feat, ind)], dim=-1)
     return out.permute(0, 3, 2, 1).contiguous()

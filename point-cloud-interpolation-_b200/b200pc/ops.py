@@ -173,6 +173,75 @@ def gather(points, idx):
 
 
 # ------------------------------------------------------------------------------------------
+def _group_raw(xyz, new_xyz, feat, idx, xyz_first):
+    B, N, _ = xyz.shape
+    S, K = idx.shape[1], idx.shape[2]
+    D = 0 if feat is None else feat.shape[2]
+    out = torch.empty(B, 3 + D, K, S, dtype=torch.float32, device=xyz.device)
+    if CHECK_BOUNDS and idx.numel() and (int(idx.min()) < -N or int(idx.max()) >= N):
+        raise IndexError("index out of range in group_points (valid range is [-%d, %d))" % (N, N))
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().b200pc_group_points(_ptr(xyz), _ptr(new_xyz), _ptr(feat if D else None), _ptr(idx), B, N, S, K,
+                                                   D, int(bool(xyz_first)), _ptr(out), _stream(xyz.device)))
+    _bump()
+    return out
+
+
+class _GroupFn(torch.autograd.Function):
+    """differentiable in the features (what the reference's models train through); the coordinates get their
+    gradient from the same three terms the unfused graph would produce, built with torch ops on the xyz channels."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, feat, idx, xyz_first):
+        ctx.save_for_backward(idx)
+        ctx.shapes = (xyz.shape, new_xyz.shape, None if feat is None else feat.shape, bool(xyz_first))
+        return _group_raw(xyz, new_xyz, feat, idx, xyz_first)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        xs, cs, fs, xyz_first = ctx.shapes
+        B, N, _ = xs
+        S, K = idx.shape[1], idx.shape[2]
+        gout = gout.contiguous()
+        gxyz = gnew = gfeat = None
+        D = 0 if fs is None else fs[2]
+        if fs is not None and ctx.needs_input_grad[2] and D:
+            gfeat = torch.zeros(B, N, D, dtype=torch.float32, device=gout.device)
+            with torch.cuda.device(gout.device):
+                _lib.check(_lib.load().b200pc_group_points_bwd(_ptr(gout), _ptr(idx), B, N, S, K, D, int(xyz_first),
+                                                               _ptr(gfeat), _stream(gout.device)))
+            _bump()
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx = gout[:, 0:3] if xyz_first else gout[:, D:D + 3]              # [B,3,K,S]
+            if ctx.needs_input_grad[1]:
+                gnew = -gx.sum(dim=2).transpose(1, 2).contiguous()            # [B,S,3]
+            if ctx.needs_input_grad[0]:
+                rows = gx.permute(0, 3, 2, 1).reshape(B, S * K, 3)
+                flat = torch.where(idx < 0, idx + N, idx).reshape(B, S * K, 1).expand(-1, -1, 3)
+                gxyz = torch.zeros(B, N, 3, dtype=torch.float32, device=gout.device).scatter_add_(1, flat, rows)
+        return gxyz, gnew, gfeat, None, None
+
+
+def group_points(xyz, new_xyz, feat, idx, xyz_first=True):
+    """Utils/Layers.py:57-66 (xyz_first) / Utils/Pointnet2Utils.py:243-253 (features first): xyz [B,N,3],
+    new_xyz [B,S,3], feat [B,N,D] or None, idx [B,S,K] -> the Conv2d input [B,3+D,K,S] in one kernel."""
+    xyz = _prep(xyz, "xyz"); new_xyz = _prep(new_xyz, "new_xyz")
+    if feat is not None:
+        feat = _prep(feat, "feat")
+        if feat.shape[2] == 0:
+            feat = None
+    idx = _idx64(idx, xyz.device)
+    if idx.dim() != 3 or idx.shape[0] != xyz.shape[0] or idx.shape[1] != new_xyz.shape[1]:
+        raise ValueError("group_points: idx must be [B,S,K] with S = new_xyz.shape[1], got %s" % (tuple(idx.shape),))
+    if feat is not None and (feat.shape[0] != xyz.shape[0] or feat.shape[1] != xyz.shape[1]):
+        raise ValueError("group_points: feat must be [B,N,D] with the same B, N as xyz")
+    needs = torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad or (feat is not None and feat.requires_grad))
+    if needs:
+        return _GroupFn.apply(xyz, new_xyz, feat, idx, xyz_first)
+    return _group_raw(xyz, new_xyz, feat, idx, xyz_first)
+
+
 def three_nn(unknown, known, variant=0, want_weight=True):
     """three nearest `known` points for every `unknown` point.
     -> dist [B,N,3] (ascending raw expanded-form values), idx [B,N,3] int64, weight [B,N,3]."""

@@ -77,7 +77,7 @@ def cuda_backend(tape=None):
     from . import ops, pointnet2_utils as P, pytorch3d_shim as S
     be = types.SimpleNamespace(
         index_points=P.index_points, query_ball_point=P.query_ball_point, knn_point=P.knn_point,
-        three_nn_weights=P.three_nn_weights, three_interpolate=P.three_interpolate,
+        three_nn_weights=P.three_nn_weights, three_interpolate=P.three_interpolate, group_points=P.group_points,
         knn_points=S.knn_points, knn_gather=S.knn_gather, tape=tape)
     if tape is None:
         be.farthest_point_sample = P.farthest_point_sample
@@ -137,6 +137,9 @@ def _group(be, refs_cf, centres_cf, feats_cf, nsample, radius=None):
         idx = be.knn_point(nsample, refs, centres)
     else:
         idx = be.query_ball_point(radius, nsample, refs, centres)
+    fused = getattr(be, "group_points", None)
+    if fused is not None:                                                 # one kernel instead of 2 gathers, sub, cat, permute
+        return fused(refs, centres, feats, idx)
     rel = be.index_points(refs, idx) - centres.view(B, S, 1, 3)
     out = torch.cat([rel, be.index_points(feats, idx)], dim=-1)          # [B,S,ns,3+D]
     return out.permute(0, 3, 2, 1).contiguous()

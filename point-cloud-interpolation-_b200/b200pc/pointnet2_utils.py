@@ -72,3 +72,10 @@ def three_nn_weights(unknown, known, variant=0):
 def three_interpolate(feats, idx, weight):
     """feats [B,S,C], idx [B,N,3], weight [B,N,3] -> [B,N,C]; differentiable in feats and weight."""
     return ops.three_interpolate(feats, idx, weight)
+
+
+def group_points(xyz, new_xyz, features, idx, xyz_first=True):
+    """Fused tail of Group.forward (Utils/Layers.py:57-66) / the SA-MSG grouping (Utils/Pointnet2Utils.py:243-253):
+    index_points(xyz, idx) - new_xyz.view(B,S,1,3), index_points(features, idx), cat, permute(0,3,2,1).contiguous()
+    -> [B,3+D,K,S] in one kernel.  Point-major inputs (xyz [B,N,3], new_xyz [B,S,3], features [B,N,D] or None)."""
+    return ops.group_points(xyz, new_xyz, features, idx, xyz_first)

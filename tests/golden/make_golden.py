@@ -12,6 +12,7 @@ these vectors are the pin for oracle/strict.c and oracle/ref_torch.py:
   gather      Utils.Pointnet2Utils.index_points                            (file :44)
   knn         Utils.Layers.Group(knn=True).forward, indices recovered by passing the point index
               as a feature channel                                         (Layers.py:42-66)
+  group       Utils.Layers.Group.forward, whole output tensor [B,3+D,ns,S] as a digest      (Layers.py:42-66)
   fp_a        Utils.Layers.FeaturePropagation.forward with its conv stack replaced by Identity on the
               instance, identity-matrix features -> per-point weight rows  (Layers.py:174-192)
   fp_b        Utils.Pointnet2Utils.PointNetFeaturePropagation(mlp=[]).forward   (file :279-313)
@@ -87,6 +88,16 @@ def main():
         grp = L.Group(None, k, knn=True)
         o = grp(pts, new, fidx)                                          # [B,3+1,k,S]
         out["knn_k%d_q%d_r%d" % (k, nq, nr)] = o[:, 3].permute(0, 2, 1).round().numpy().astype(np.int32)
+
+    # ---- the full Group.forward output (gather, centre, cat, permute) with real feature channels ----
+    featg = torch.from_numpy(np.random.default_rng(6).normal(size=(2, 5, 4096)).astype(np.float32))     # [B,D=5,N]
+    new512 = Bt[:, :512].permute(0, 2, 1).contiguous()
+    ptsg = A.permute(0, 2, 1).contiguous()
+    out["group_feat_seed6"] = np.array([6, 5], np.int32)                 # rng seed, D
+    # kNN variant: topk's order among exactly tied distances is unspecified, so the tensor itself is stored (48 centres)
+    out["group_knn16_q48"] = L.Group(None, 16, knn=True)(ptsg, new512[:, :, :48].contiguous(), featg).numpy()   # [2,8,16,48]
+    self512 = A[:, ::8].permute(0, 2, 1).contiguous()                    # centres taken from the refs (SetConv): no empty ball
+    out["group_ball_self_r1_ns32_sha"] = digest(L.Group(1.0, 32, knn=False)(ptsg, self512, featg).numpy())   # [2,8,32,512]
 
     # ---- three-NN + interpolation, variant A: FeaturePropagation ---------------------------
     S, N = 64, 1024

@@ -165,3 +165,62 @@ def test_chamfer_loss_reference_layout(cuda_dev):
     loss, _ = S3.chamfer_distance(pc1.permute(0, 2, 1), pc2.permute(0, 2, 1))
     ol = strict.chamfer(a, b)[0]
     assert abs(loss.item() - ol) <= 1e-5 * abs(ol)
+
+
+# ---------------------------------------------------------------- fused grouping
+@pytest.mark.parametrize("xyz_first", [True, False])
+@pytest.mark.parametrize("B,N,S,K,D", [(2, 4096, 512, 16, 5),     # the golden fixture's shape
+                                       (1, 1024, 256, 16, 3),     # SetConv 1 of FlowNet3D
+                                       (2, 256, 256, 64, 128),    # FlowEmbedding
+                                       (1, 300, 77, 3, 0),        # ragged S, no feature channels
+                                       (1, 64, 33, 8, 300),       # more channels than one shared-memory pass (256)
+                                       (3, 50, 1, 1, 2)])
+def test_group_points_bit_exact(cuda_dev, B, N, S, K, D, xyz_first):
+    a, b = synth.batch_pairs(40, B, max(N, S))
+    xyz, new = a[:, :N].copy(), b[:, :S].copy()
+    rng = np.random.default_rng(41)
+    feat = rng.normal(size=(B, N, D)).astype(np.float32) if D else None
+    idx = rng.integers(0, N, size=(B, S, K))
+    out = P.group_points(_t(xyz, cuda_dev), _t(new, cuda_dev), None if feat is None else _t(feat, cuda_dev), _t(idx, cuda_dev), xyz_first)
+    want = strict.group_points(xyz, new, feat, idx, xyz_first)
+    assert out.shape == want.shape == (B, 3 + D, K, S) and out.is_contiguous()
+    np.testing.assert_array_equal(_bits(out.cpu().numpy()), _bits(want))
+
+
+def test_group_points_equals_the_unfused_reference_ops(cuda_dev):
+    # the five ops of Group.forward (Utils/Layers.py:57-66) on the same kernels' outputs, including negative indices
+    a, b = synth.batch_pairs(42, 2, 2048)
+    xyz, new = _t(a, cuda_dev), _t(b[:, :300], cuda_dev)
+    feat = torch.randn(2, 2048, 20, device=cuda_dev)
+    idx = P.query_ball_point(2.0, 24, xyz, new)
+    idx[0, :5] -= 2048                                                                  # python-style negative indices wrap
+    rel = P.index_points(xyz, idx) - new.view(2, 300, 1, 3)
+    want = torch.cat([rel, P.index_points(feat, idx)], dim=-1).permute(0, 3, 2, 1).contiguous()
+    assert torch.equal(P.group_points(xyz, new, feat, idx), want)
+
+
+def test_group_points_backward_matches_unfused_autograd(cuda_dev):
+    a, b = synth.batch_pairs(43, 2, 1024)
+    idx = torch.randint(0, 1024, (2, 200, 12), device=cuda_dev)
+    gout = torch.randn(2, 3 + 16, 12, 200, device=cuda_dev)
+    grads = []
+    for fused in (True, False):
+        xyz = _t(a, cuda_dev).requires_grad_(True); new = _t(b[:, :200], cuda_dev).requires_grad_(True)
+        feat = torch.randn(2, 1024, 16, device=cuda_dev, generator=torch.Generator(cuda_dev).manual_seed(5)).requires_grad_(True)
+        if fused:
+            out = P.group_points(xyz, new, feat, idx)
+        else:
+            rel = xyz[torch.arange(2, device=cuda_dev).view(2, 1, 1), idx] - new.view(2, 200, 1, 3)
+            out = torch.cat([rel, feat[torch.arange(2, device=cuda_dev).view(2, 1, 1), idx]], dim=-1).permute(0, 3, 2, 1)
+        out.backward(gout)
+        grads.append((xyz.grad, new.grad, feat.grad))
+    for g_fused, g_ref in zip(*grads):
+        torch.testing.assert_close(g_fused, g_ref, rtol=1e-5, atol=1e-5)                # fp32 sums in a different order
+
+
+def test_group_points_rejects_bad_shapes(cuda_dev):
+    xyz = torch.zeros(1, 10, 3, device=cuda_dev); new = torch.zeros(1, 4, 3, device=cuda_dev)
+    with pytest.raises(ValueError):
+        P.group_points(xyz, new, None, torch.zeros(1, 5, 2, dtype=torch.long, device=cuda_dev))
+    with pytest.raises(RuntimeError):
+        P.group_points(xyz.cpu(), new, None, torch.zeros(1, 4, 2, dtype=torch.long))

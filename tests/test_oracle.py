@@ -209,3 +209,40 @@ def test_real_reference_agrees_with_oracle_live():
 def test_real_reference_layers_import_with_stubs():
     L = ref_loader.layers()
     assert hasattr(L, "Group") and hasattr(L, "FeaturePropagation") and hasattr(L, "PointsFusion")
+
+
+# ---------------------------------------------------------------- fused grouping
+def _group_inputs(pair100):
+    a, b = pair100
+    seed, D = (int(v) for v in GOLD["group_feat_seed6"])
+    feat = np.random.default_rng(seed).normal(size=(2, D, 4096)).astype(np.float32).transpose(0, 2, 1).copy()   # [B,N,D]
+    return a, b, feat
+
+
+def test_golden_group_forward_ball(pair100):
+    # the WHOLE output of the real Group.forward (ball query, centres taken from the refs), as a digest
+    a, _, feat = _group_inputs(pair100)
+    centres = np.ascontiguousarray(a[:, ::8])
+    idx = strict.query_ball_point(1.0, 32, a, centres)
+    assert np.array_equal(sha(strict.group_points(a, centres, feat, idx)), GOLD["group_ball_self_r1_ns32_sha"])
+
+
+def test_golden_group_forward_knn(pair100):
+    a, b, feat = _group_inputs(pair100)
+    qry = np.ascontiguousarray(b[:, :48])
+    clean = tie_free_rows(a, qry, 16, strict.FORM_KNN)           # topk's order among exact ties is unspecified
+    assert clean.mean() > 0.9
+    mine = strict.group_points(a, qry, feat, strict.knn_point(16, a, qry))        # [B,8,16,S]
+    gold = GOLD["group_knn16_q48"]
+    assert mine.shape == gold.shape == (2, 8, 16, 48)
+    for bi in range(2):
+        assert np.array_equal(bits(mine[bi][:, :, clean[bi]]), bits(gold[bi][:, :, clean[bi]]))
+
+
+def test_group_points_feature_first_order_and_no_features(pair100):
+    a, b, feat = _group_inputs(pair100)
+    qry = np.ascontiguousarray(b[:, :64]); idx = strict.knn_point(4, a, qry)
+    x = strict.group_points(a, qry, feat, idx, xyz_first=True); f = strict.group_points(a, qry, feat, idx, xyz_first=False)
+    assert x.shape == f.shape == (2, 8, 4, 64)
+    assert np.array_equal(x[:, :3], f[:, 5:]) and np.array_equal(x[:, 3:], f[:, :5])      # SA-MSG puts the features first
+    assert np.array_equal(strict.group_points(a, qry, None, idx), x[:, :3])
