@@ -214,6 +214,18 @@ def extras(dev, a, b, flush):
     ibytes = B3 * NPTS * 128 * 4 + B3 * 4096 * 128 * 4 + B3 * NPTS * (24 + 12)
     out["three_interpolate_c3"] = {"ms": s * 1e3, "gb_per_s": ibytes / s / 1e9, "hbm_frac": ibytes / s / 1e9 / hbm,
                                    "algorithmic_bytes": ibytes}
+    # fused grouping on the C3 clouds: 4096 centres x 16 neighbours, D=64 feature channels
+    gfeat = feats[:, :, :64].contiguous()
+    gidx = P.knn_point(16, xyz, known)
+    s = t(lambda: P.group_points(xyz, known, gfeat, gidx))
+
+    def unfused():          # the reference's five ops (Utils/Layers.py:57-66) on this repo's own gather kernels
+        rel = P.index_points(xyz, gidx) - known.view(B3, 4096, 1, 3)
+        return torch.cat([rel, P.index_points(gfeat, gidx)], dim=-1).permute(0, 3, 2, 1).contiguous()
+    su = t(unfused)
+    gb = B3 * 4096 * 16 * (8 + 4 * 67) + B3 * NPTS * 4 * 67 + B3 * 4096 * 12     # idx + output + each table row once + centres
+    out["group_points_c3"] = {"ms": s * 1e3, "gb_per_s": gb / s / 1e9, "hbm_frac": gb / s / 1e9 / hbm, "algorithmic_bytes": gb,
+                              "unfused_ms": su * 1e3, "shape": "B=16 N=16384 S=4096 K=16 D=64 -> [16,67,16,4096]"}
     # Chamfer, C4 per-GPU share: 4 pairs x 8192 points
     x = ref[:4, :8192].contiguous(); y = qry[:4, :8192].contiguous()
     s = t(lambda: ops.chamfer(x, y))

@@ -173,7 +173,8 @@ def test_chamfer_loss_reference_layout(cuda_dev):
                                        (1, 1024, 256, 16, 3),     # SetConv 1 of FlowNet3D
                                        (2, 256, 256, 64, 128),    # FlowEmbedding
                                        (1, 300, 77, 3, 0),        # ragged S, no feature channels
-                                       (1, 64, 33, 8, 300),       # more channels than one shared-memory pass (256)
+                                       (1, 64, 33, 8, 300),       # wide rows (16-byte row reads)
+                                       (2, 128, 70, 5, 37),       # D not a multiple of 4: scalar row reads
                                        (3, 50, 1, 1, 2)])
 def test_group_points_bit_exact(cuda_dev, B, N, S, K, D, xyz_first):
     a, b = synth.batch_pairs(40, B, max(N, S))
