@@ -1,5 +1,5 @@
 """Tiny driver for ncu captures: runs ONE op of the hot path a few times on synthetic C2/C3 inputs.
-usage: python tools/prof_driver.py {knn|ball|three_nn|knn_direct|fps|gather|interp|chamfer} [reps]"""
+usage: python tools/prof_driver.py {knn|ball|three_nn|knn_direct|nn1|fps|gather|interp|group|chamfer} [reps]"""
 import os
 import sys
 
@@ -35,6 +35,10 @@ elif op == "interp":
     feats = torch.randn(B, 4096, 128, device=dev)
     known = ref[:, ::4].contiguous(); _, i3, w3 = P.three_nn_weights(ref, known)
     fn = lambda: P.three_interpolate(feats, i3, w3)
+elif op == "group":
+    feats = torch.randn(B, 16384, 64, device=dev); known = ref[:, ::4].contiguous()
+    gidx = P.knn_point(16, ref, known)
+    fn = lambda: P.group_points(ref, known, feats, gidx)
 elif op == "chamfer":
     fn = lambda: ops.chamfer(ref[:, :8192].contiguous(), qry[:, :8192].contiguous())
 else:
