@@ -124,6 +124,16 @@ int b200pc_group_points(const float *xyz, const float *new_xyz, const float *fea
 int b200pc_group_points_bwd(const float *grad_out, const int64_t *idx, int B, int N, int S, int K, int D,
                             int xyz_first, float *grad_feat, b200pc_stream_t stream);
 
+/* ---- f4: PolyPCI polynomial fit + evaluation  ---------------------------
+ *      PolyPCI/Models/Models_V1.py:116-124 (fitting_and_predict), call site :191-219           */
+/* frames: HOST array of F (<= 16) device pointers, each a [B,per_batch] fp32 tensor (per_batch = 3*N for [B,3,N]
+ * frames, in the reference's stacking order: key, forward 0, backward 0, forward 1, ...);
+ * weights: device [B,F] float64, the least-squares weights of each batch item (linear in the data:
+ * value = sum_f w[f] * frame_f -- see b200pc.polypci.poly_weights);  out [B,per_batch] fp32 =
+ * (float) sum_f weights[b,f] * (double) frames[f][b,:], accumulated in float64 like numpy.           */
+int b200pc_poly_predict(const float *const *frames, const double *weights, int B, int F, int64_t per_batch, float *out,
+                        b200pc_stream_t stream);
+
 /* ---- a9: chamfer_loss  Utils/Utils.py:39-48 -> pytorch3d.loss.chamfer_distance defaults --- */
 /* x [B,N,3], y [B,M,3].  Outputs: per-point nearest squared distance and index in both
  * directions (dx,ix: [B,N]; dy,iy: [B,M]) and the scalar loss[1] =

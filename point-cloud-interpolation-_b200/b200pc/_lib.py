@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200pc_gather": (_i, [_p, _p, _i, _i, _i, _l, _p, _p, _p]),
     "b200pc_gather_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p, _p]),
     "b200pc_group_points": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "b200pc_poly_predict": (_i, [_p, _p, _i, _i, _l, _p, _p]),
     "b200pc_group_points_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "b200pc_chamfer_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
     "b200pc_chamfer_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),

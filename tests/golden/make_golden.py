@@ -16,6 +16,7 @@ these vectors are the pin for oracle/strict.c and oracle/ref_torch.py:
   fp_a        Utils.Layers.FeaturePropagation.forward with its conv stack replaced by Identity on the
               instance, identity-matrix features -> per-point weight rows  (Layers.py:174-192)
   fp_b        Utils.Pointnet2Utils.PointNetFeaturePropagation(mlp=[]).forward   (file :279-313)
+  polyfit     PolyPCI.Models.Models_V1.PolyPCI.fitting_and_predict (function source executed) (:116-124)
 
 Outputs that are large are stored as int32 / as SHA-256 digests of their bytes.
 """
@@ -116,6 +117,22 @@ def main():
     # ---- variant B: PointNetFeaturePropagation with an empty MLP ---------------------------
     pfp = R.PointNetFeaturePropagation(32, [])
     out["fp_b_out"] = pfp(dense.permute(0, 2, 1), sparse.permute(0, 2, 1), None, featC).numpy()
+
+    # ---- PolyPCI polynomial fit: the REAL fitting_and_predict, extracted from the file's AST (the module itself
+    # imports datasets / visualisers that are not installed) and executed on seeded frames ---------------------------
+    import ast
+    import types
+    from sklearn.preprocessing import PolynomialFeatures
+    src = open(os.path.join(ref_loader.REF_ROOT, "PolyPCI", "Models", "Models_V1.py")).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "fitting_and_predict")
+    ns = {"np": np, "PolynomialFeatures": PolynomialFeatures}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "Models_V1.py", "exec"), ns)
+    prng = np.random.default_rng(9)
+    for tag, T, tq, deg in (("f5_d3", [0.0, -1.0, 1.0, -2.0, 2.0], 0.5, 3), ("f7_d2", [0.0, -1.0, 1.0, -2.0, 2.0, -3.0, 3.0], -0.25, 2)):
+        frames = (prng.normal(size=(len(T), 96)) * 30).astype(np.float32)              # [F,N], seed 9, drawn in this order
+        val = ns["fitting_and_predict"](types.SimpleNamespace(degree=deg), np.array(T).reshape(-1), frames, torch.tensor(tq))
+        out["polyfit_%s" % tag] = torch.tensor(val).to(torch.float32).numpy()           # like Models_V1.py:198
+        out["polyfit_%s_T" % tag] = np.array(T, np.float64); out["polyfit_%s_t" % tag] = np.array([tq, deg], np.float64)
 
     path = os.path.join(HERE, "reference_outputs.npz")
     np.savez_compressed(path, **out)

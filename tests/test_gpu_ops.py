@@ -225,3 +225,31 @@ def test_group_points_rejects_bad_shapes(cuda_dev):
         P.group_points(xyz, new, None, torch.zeros(1, 5, 2, dtype=torch.long, device=cuda_dev))
     with pytest.raises(RuntimeError):
         P.group_points(xyz.cpu(), new, None, torch.zeros(1, 4, 2, dtype=torch.long))
+
+
+# ---------------------------------------------------------------- PolyPCI polynomial fit
+@pytest.mark.parametrize("B,N,field,degree", [(2, 4096, 2, 3), (1, 16384, 3, 2), (3, 1001, 1, 1)])
+def test_poly_fit_and_predict_matches_host_restatement(cuda_dev, B, N, field, degree):
+    from b200pc import polypci
+    from oracle import ref_polyfit
+    F = 2 * field + 1
+    rng = np.random.default_rng(50 + N)
+    base = (rng.normal(size=(B, 3, N)) * 30).astype(np.float32)
+    frames = [(base + rng.normal(size=(B, 3, N)).astype(np.float32) * (0.3 * f)).astype(np.float32) for f in range(F)]
+    T_list = [[0.0] + [s * (i + 1) for i in range(field) for s in (-1.0, 1.0)] for _ in range(B)]   # key, fwd0, bwd0, fwd1, ...
+    t = np.linspace(-0.5, 0.7, B)
+    out = polypci.fit_and_predict([_t(f, cuda_dev) for f in frames], T_list, torch.from_numpy(t), degree)
+    want = ref_polyfit.forward_tail(frames, T_list, t, degree)
+    assert out.shape == (B, 3, N) and out.dtype == torch.float32
+    # float64 accumulation on both sides, in a different association: fp32 results agree to the last bit or one ulp
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+
+
+def test_poly_fit_rejects_cpu_and_bad_counts(cuda_dev):
+    from b200pc import polypci
+    f = [torch.zeros(1, 3, 8) for _ in range(3)]
+    with pytest.raises(RuntimeError):
+        polypci.fit_and_predict(f, [[0.0, -1.0, 1.0]], [0.5], 1)
+    g = [x.to(cuda_dev) for x in f]
+    with pytest.raises(ValueError):
+        polypci.fit_and_predict(g, [[0.0, -1.0]], [0.5], 1)

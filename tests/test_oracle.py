@@ -246,3 +246,27 @@ def test_group_points_feature_first_order_and_no_features(pair100):
     assert x.shape == f.shape == (2, 8, 4, 64)
     assert np.array_equal(x[:, :3], f[:, 5:]) and np.array_equal(x[:, 3:], f[:, :5])      # SA-MSG puts the features first
     assert np.array_equal(strict.group_points(a, qry, None, idx), x[:, :3])
+
+
+# ---------------------------------------------------------------- PolyPCI polynomial fit
+def _polyfit_case(tag):
+    T = GOLD["polyfit_%s_T" % tag]; tq, deg = GOLD["polyfit_%s_t" % tag]
+    return T, float(tq), int(deg)
+
+
+def test_golden_polyfit_restatement_and_linear_weights():
+    from oracle import ref_polyfit
+    from b200pc import polypci
+    prng = np.random.default_rng(9)                                        # same draws, same order as make_golden.py
+    for tag in ("f5_d3", "f7_d2"):
+        T, tq, deg = _polyfit_case(tag)
+        frames = (prng.normal(size=(len(T), 96)) * 30).astype(np.float32)
+        gold = GOLD["polyfit_%s" % tag]
+        mine = ref_polyfit.fitting_and_predict(T, frames, tq, deg).astype(np.float32)
+        # same numpy calls as the real function: identical up to the LAPACK build of the machine running the test
+        np.testing.assert_allclose(mine, gold, rtol=2e-6, atol=1e-6)
+        # the product's formulation: ONE weight vector per batch item (least squares is linear in the data)
+        w = polypci.poly_weights(T, tq, deg)
+        assert w.shape == (len(T),) and w.dtype == np.float64
+        np.testing.assert_allclose((w @ frames.astype(np.float64)).astype(np.float32)[None], gold, rtol=2e-6, atol=1e-6)
+        assert abs(w.sum() - 1.0) < 1e-12                                 # a polynomial fit reproduces constants
