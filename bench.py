@@ -226,20 +226,20 @@ def extras(dev, a, b, flush):
     gb = B3 * 4096 * 16 * (8 + 4 * 67) + B3 * NPTS * 4 * 67 + B3 * 4096 * 12     # idx + output + each table row once + centres
     out["group_points_c3"] = {"ms": s * 1e3, "gb_per_s": gb / s / 1e9, "hbm_frac": gb / s / 1e9 / hbm, "algorithmic_bytes": gb,
                               "unfused_ms": su * 1e3, "shape": "B=16 N=16384 S=4096 K=16 D=64 -> [16,67,16,4096]"}
-    # PolyPCI polynomial fit at the C5 size: 2 items x 65536 points, 5 frames, degree 3
+    # PolyPCI polynomial fit at the C5 size: 65536 points, field 2 (5 frames), T=[0,-1,1,-2,2], t=0.5, degree 2
     try:
         from b200pc import polypci
-        fr = [torch.randn(2, 3, 65536, device=dev) * 30 for _ in range(5)]
-        Tl = [[0.0, -1.0, 1.0, -2.0, 2.0]] * 2
-        tq = torch.tensor([0.5, -0.25])
-        s = t(lambda: polypci.fit_and_predict(fr, Tl, tq, 3))
-        pb = 6 * 4 * 2 * 3 * 65536
+        fr = [torch.randn(1, 3, 65536, device=dev) * 30 for _ in range(5)]
+        Tl = [[0.0, -1.0, 1.0, -2.0, 2.0]]
+        tq = torch.tensor([0.5])
+        s = t(lambda: polypci.fit_and_predict(fr, Tl, tq, 2))
+        pb = 6 * 4 * 3 * 65536
         out["poly_fit_predict_c5"] = {"ms": s * 1e3, "gb_per_s": pb / s / 1e9, "algorithmic_bytes": pb,
-                                      "note": "includes the host-side float64 weight solve (np.polyfit on a 5x5 identity per item)"}
+                                      "note": "includes the host-side float64 weight solve (np.polyfit on a 5x5 identity)"}
         from oracle import ref_polyfit                                    # CPU baseline leg: the reference's host path
         host = [f.cpu().numpy() for f in fr]
         t0 = time.perf_counter()
-        back = torch.from_numpy(ref_polyfit.forward_tail([f.cpu().numpy() for f in fr], Tl, tq.numpy(), 3)).to(dev)
+        back = torch.from_numpy(ref_polyfit.forward_tail([f.cpu().numpy() for f in fr], Tl, tq.numpy(), 2)).to(dev)
         torch.cuda.synchronize()
         out["poly_fit_predict_c5"]["reference_host_path_ms"] = (time.perf_counter() - t0) * 1e3   # D2H + np.polyfit + H2D
         del host, back
