@@ -322,6 +322,20 @@ def pointinet_bench(dev, rank, steps, flush, barrier, dist):
         if dist is not None:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         out[name] = float(tm.item())
+    if dist is None:
+        # throughput mode, one GPU only: 8 frame pairs per replay (FPS runs 8 clusters side by side, PointsFusion's
+        # per-item loop collapses into batched searches).  Not the C1 configuration (batch 1).
+        try:
+            del graphed
+            B8 = 8
+            ins8 = [torch.cat(x, 0) for x in zip(*[pointinet_inputs(100 + i, NPTS, dev=dev)[:4] for i in range(B8)])]
+            g8 = pointinet.GraphedPointINet(state_dict=net.state_dict(), batch=B8, npoints=NPTS, extra=1, t=0.5, device=dev)
+            g8.capture(*ins8)
+            torch.manual_seed(3000)
+            secs = timed_steps(lambda: g8(*ins8), 5, 3, flush, torch.cuda.synchronize, barrier)
+            out["graph_batch8_per_frame"] = secs / 5 / B8
+        except Exception as e:  # pragma: no cover
+            print("pointinet batch-8 measurement failed: %r" % (e,), file=sys.stderr)
     return out
 
 
@@ -466,6 +480,9 @@ def main():
                              "ms_per_frame": pn["graph"] * 1e3, "ms_per_frame_e2e": pn["graph_e2e"] * 1e3, "ms_per_frame_eager": pn["eager"] * 1e3,
                              "note": "value/e2e_value: forward captured as one CUDA graph (RNG tape, folded BatchNorm); eager_value: per-op dispatch like the reference",
                              "paper_rtx2060_frames_per_s": 4.9}
+        if "graph_batch8_per_frame" in pn:
+            line["pointinet"]["batch8_frames_per_s"] = 1.0 / pn["graph_batch8_per_frame"]
+            line["pointinet"]["batch8_note"] = "throughput mode, NOT the C1 configuration: 8 frame pairs per graph replay on one GPU"
         if world == 1:
             try:
                 csec, cthr = pointinet_cpu_baseline()

@@ -237,6 +237,7 @@ class PointsFusion(nn.Module):
         super().__init__()
         self.be = be
         self.conv = _pointwise_mlp([cin, *couts])
+        self.batched = True          # False: always the reference's per-item loop (tests compare the two)
 
     def _neighbours(self, query_cf, ref_cf, ref_feat_cf, k):
         q, r = _rows(query_cf), _rows(ref_cf)
@@ -252,6 +253,22 @@ class PointsFusion(nn.Module):
         if t_host is None:
             t_host = t.detach().reshape(B).to("cpu", torch.float32)        # device->host sync, as in the reference
         rp = getattr(self.be, "randperm", None) or (lambda n, keep, device: torch.randperm(n)[:keep].to(device))
+        if self.batched and B > 1 and all(float(t_host[i]) == float(t_host[0]) for i in range(B)):
+            # one time stamp for the whole batch -> every item has the same (n1, n2, k1, k2), so the
+            # per-item loop of the reference (upstream layers.py:389-411) collapses into two batched searches.  The
+            # random subsets are still drawn item by item in the reference's order; each item's result is unchanged.
+            n2 = int(N * t_host[0]); n1 = N - n2
+            k2 = int(k * t_host[0]); k1 = k - k2
+            s1, s2 = [], []
+            for i in range(B):
+                s1.append(rp(N, n1, xyz1.device)); s2.append(rp(N, n2, xyz1.device))
+            pick = lambda x, sel: x.gather(2, torch.stack(sel).unsqueeze(1).expand(-1, 3, -1))
+            mixed = torch.cat((pick(xyz1, s1), pick(xyz2, s2)), dim=-1)
+            (f1, g1, e1), (f2, g2, e2) = _concurrently(lambda: self._neighbours(mixed, xyz1, feats1, k1),
+                                                     lambda: self._neighbours(mixed, xyz2, feats2, k2), mixed, "fusion")
+            feat, grouped, extra = torch.cat((f1, f2), dim=-1), torch.cat((g1, g2), dim=-1), torch.cat((e1, e2), dim=-1)
+            w = F.softmax(self.conv(feat).max(dim=1)[0], dim=-1)
+            return (w.unsqueeze(1) * torch.cat([grouped, extra], dim=1)).sum(dim=-1)
         fa, ga, ea = [], [], []
         for i in range(B):
             n2 = int(N * t_host[i]); n1 = N - n2

@@ -132,3 +132,24 @@ def test_flownet3d_training_step_gradients_match_cpu_port(cuda_dev):
     assert (torch.dot(all_c, all_g) / (all_c.norm() * all_g.norm())).item() > 0.999
     assert abs(all_c.norm().item() - all_g.norm().item()) <= 2e-2 * all_c.norm().item()
     assert checked > 40
+
+
+def test_batched_points_fusion_equals_per_item_loop_gpu(cuda_dev):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = pointinet.PointINet().eval().to(cuda_dev)
+    p1, p2, f1, f2 = _inputs(4096)
+    rep = lambda x, s: torch.cat([x, x.roll(s, dims=2) * 1.01, x.roll(2 * s + 1, dims=2) * 0.99], 0).contiguous().to(cuda_dev)
+    P1, P2, F1, F2 = rep(p1, 7), rep(p2, 11), rep(f1, 0), rep(f2, 0)
+    tt = torch.tensor([0.5, 0.5, 0.5], device=cuda_dev)
+    outs = []
+    for batched in (True, False):
+        net.fusion.batched = batched
+        torch.manual_seed(3000)
+        with torch.no_grad():
+            outs.append(net(P1, P2, F1, F2, tt))
+    assert outs[0].shape == (3, 4, 4096)
+    # identical neighbour sets; the MLP runs on one [3,...] tensor instead of three [1,...] ones (cuDNN summation order)
+    err = (outs[0] - outs[1]).abs().amax(dim=1).reshape(-1)
+    assert (err < 1e-4).float().mean() > 0.999, "only %.4f of the points agree" % (err < 1e-4).float().mean()

@@ -69,3 +69,28 @@ def test_flownet3d_equals_upstream_on_cpu():
     with torch.no_grad():
         got = mine(p1, p2, f1, f2)
     torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_batched_points_fusion_equals_per_item_loop_cpu():
+    # with one time stamp for the batch, the per-item loop of PointsFusion (upstream layers.py:389-411)
+    # collapses into two batched searches; same RNG draws in the same order, so every item's output is unchanged
+    torch.manual_seed(0)
+    net = pointinet.PointINet(backend=cpu_backend.make()).eval()
+    p1, p2, f1, f2 = _inputs()
+    rep = lambda x, s: torch.cat([x, x.roll(s, dims=2) * 1.01], 0).contiguous()          # two different items
+    P1, P2, F1, F2 = rep(p1, 7), rep(p2, 11), rep(f1, 0), rep(f2, 0)
+    tt = torch.tensor([0.3, 0.3], dtype=torch.float32)
+    outs = []
+    for batched in (True, False):
+        net.fusion.batched = batched
+        torch.manual_seed(3000)
+        with torch.no_grad():
+            outs.append(net(P1, P2, F1, F2, tt))
+    assert outs[0].shape == (2, 4, 2048)
+    torch.testing.assert_close(outs[0], outs[1], rtol=1e-6, atol=1e-6)
+    # different time stamps inside one batch keep the loop
+    net.fusion.batched = True
+    torch.manual_seed(3000)
+    with torch.no_grad():
+        mixed_t = net(P1, P2, F1, F2, torch.tensor([0.3, 0.6]))
+    assert mixed_t.shape == (2, 4, 2048) and torch.isfinite(mixed_t).all()
