@@ -104,7 +104,7 @@ def test_index_points_backward_scatter_add(cuda_dev):
 
 
 # ---------------------------------------------------------------- three_interpolate (a5)
-@pytest.mark.parametrize("C", [128, 256, 3, 30])
+@pytest.mark.parametrize("C", [128, 256, 3, 30, 64, 12])
 def test_three_interpolate_forward(cuda_dev, C):
     a, _ = synth.batch_pairs(80, 2, 4096)
     known = a[:, ::8].copy()
