@@ -128,10 +128,13 @@ def _rows(t):
     return t.transpose(1, 2).contiguous()
 
 
-def _group(be, refs_cf, centres_cf, feats_cf, nsample, radius=None):
+def _group(be, refs_cf, centres_cf, feats_cf, nsample, radius=None, refs_rows=None, centres_rows=None):
     """neighbourhoods of `centres` in `refs` -> [B, 3+D, nsample, S]: relative xyz then features.
-    radius=None selects kNN (flow embedding / up-conv), else the ball query (set conv)."""
-    refs, centres, feats = _rows(refs_cf), _rows(centres_cf), _rows(feats_cf)
+    radius=None selects kNN (flow embedding / up-conv), else the ball query (set conv).  Callers that already hold
+    the point-major copies pass them in (the reference re-permutes the same tensors in every layer)."""
+    refs = _rows(refs_cf) if refs_rows is None else refs_rows
+    centres = _rows(centres_cf) if centres_rows is None else centres_rows
+    feats = _rows(feats_cf)
     B, S, _ = centres.shape
     if radius is None:
         idx = be.knn_point(nsample, refs, centres)
@@ -153,8 +156,9 @@ class SetConv(nn.Module):
 
     def forward(self, xyz, feats):
         rows = _rows(xyz)
-        centres = _rows(self.be.index_points(rows, self.be.farthest_point_sample(rows, self.npoint)))
-        g = _group(self.be, xyz, centres, feats, self.nsample, self.radius)
+        centre_rows = self.be.index_points(rows, self.be.farthest_point_sample(rows, self.npoint))     # [B,S,3]
+        centres = _rows(centre_rows)
+        g = _group(self.be, xyz, centres, feats, self.nsample, self.radius, refs_rows=rows, centres_rows=centre_rows)
         return centres, self.conv(g).max(dim=2)[0]
 
 
