@@ -97,6 +97,11 @@ int b200pc_three_interpolate_bwd(const float *gout, const float *feat, const int
 int b200pc_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, void *workspace,
                size_t workspace_bytes, b200pc_stream_t stream);
 
+/* a7: Sample.forward (Utils/Layers.py:23-27) = farthest_point_sample + index_points(points, ind): the same kernel also
+ * writes the coordinates of every pick, new_xyz [B,npoint,3] (bit-identical to gathering xyz with idx afterwards).   */
+int b200pc_fps_sample(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, float *new_xyz,
+                      b200pc_stream_t stream);
+
 /* ---- a6: index_points(points, idx)  Utils/Pointnet2Utils.py:44-61 ------------------------ */
 /* points [B,N,C]; idx flattened to [B,R] (R = prod(idx.shape[1:])); out [B,R,C].
  * Negative indices wrap once (python semantics).  If oob_flag != NULL, *oob_flag (device int,

@@ -32,6 +32,7 @@ SIGNATURES = {
     "b200pc_three_interpolate": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "b200pc_three_interpolate_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "b200pc_fps": (_i, [_p, _i, _i, _i, _p, _p, _p, _z, _p]),
+    "b200pc_fps_sample": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "b200pc_gather": (_i, [_p, _p, _i, _i, _i, _l, _p, _p, _p]),
     "b200pc_gather_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p, _p]),
     "b200pc_group_points": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -108,18 +108,23 @@ def ball_query(radius, nsample, xyz, new_xyz):
     return idx
 
 
-def fps(xyz, npoint, start):
-    """Utils/Pointnet2Utils.py:64  start [B] int64 (first centroid) -> [B,npoint] int64."""
+def fps(xyz, npoint, start, want_xyz=False):
+    """Utils/Pointnet2Utils.py:64  start [B] int64 (first centroid) -> [B,npoint] int64.
+    want_xyz: also return the picks' coordinates [B,npoint,3] from the same kernel (Sample.forward, Utils/Layers.py:23-27)."""
     xyz = _prep(xyz, "xyz")
     B, N, _ = xyz.shape
     dev = xyz.device
     start = _idx64(start, dev)
     idx = torch.empty(B, int(npoint), dtype=torch.int64, device=dev)
+    new_xyz = torch.empty(B, int(npoint), 3, dtype=torch.float32, device=dev) if want_xyz else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().b200pc_fps(_ptr(xyz), B, N, int(npoint), _ptr(start), _ptr(idx), C.c_void_p(0), 0,
-                                          _stream(dev)))
+        if want_xyz:
+            _lib.check(_lib.load().b200pc_fps_sample(_ptr(xyz), B, N, int(npoint), _ptr(start), _ptr(idx), _ptr(new_xyz), _stream(dev)))
+        else:
+            _lib.check(_lib.load().b200pc_fps(_ptr(xyz), B, N, int(npoint), _ptr(start), _ptr(idx), C.c_void_p(0), 0,
+                                              _stream(dev)))
     _bump()
-    return idx
+    return (idx, new_xyz) if want_xyz else idx
 
 
 # ------------------------------------------------------------------------------------------

@@ -81,9 +81,11 @@ def cuda_backend(tape=None):
         knn_points=S.knn_points, knn_gather=S.knn_gather, tape=tape)
     if tape is None:
         be.farthest_point_sample = P.farthest_point_sample
+        be.sample_points = P.sample_points
         be.randperm = lambda n, keep, device: torch.randperm(n)[:keep].to(device)
     else:
         be.farthest_point_sample = lambda xyz, npoint: ops.fps(xyz, npoint, tape.randint(xyz.shape[1], xyz.shape[0]))
+        be.sample_points = lambda xyz, npoint: ops.fps(xyz, npoint, tape.randint(xyz.shape[1], xyz.shape[0]), want_xyz=True)
         be.randperm = lambda n, keep, device: tape.randperm(n, keep)
     return be
 
@@ -156,7 +158,11 @@ class SetConv(nn.Module):
 
     def forward(self, xyz, feats):
         rows = _rows(xyz)
-        centre_rows = self.be.index_points(rows, self.be.farthest_point_sample(rows, self.npoint))     # [B,S,3]
+        sample = getattr(self.be, "sample_points", None)
+        if sample is not None:
+            _, centre_rows = sample(rows, self.npoint)                                                 # FPS + gather in one kernel
+        else:
+            centre_rows = self.be.index_points(rows, self.be.farthest_point_sample(rows, self.npoint))     # [B,S,3]
         centres = _rows(centre_rows)
         g = _group(self.be, xyz, centres, feats, self.nsample, self.radius, refs_rows=rows, centres_rows=centre_rows)
         return centres, self.conv(g).max(dim=2)[0]

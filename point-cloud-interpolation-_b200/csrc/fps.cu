@@ -38,7 +38,8 @@ struct __align__(16) FpsRecord {  // what a CTA tells its peers each round
 
 template <int P>
 __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xyz, int N, int npoint,
-                                                    const int64_t *__restrict__ start, int64_t *__restrict__ out) {
+                                                    const int64_t *__restrict__ start, int64_t *__restrict__ out,
+                                                    float *__restrict__ centres) {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -83,7 +84,13 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
 #ifdef B200PC_FPS_TIMING
         t0 = clock64();
 #endif
-        if (rank == 0 && t == 0) out[(size_t)b * npoint + it] = far;
+        if (rank == 0 && t == 0) {
+            out[(size_t)b * npoint + it] = far;
+            if (centres) {   // Sample.forward's index_points(points, ind), free: every thread already holds the pick's coordinates
+                float *c = centres + ((size_t)b * npoint + it) * 3;
+                c[0] = cx; c[1] = cy; c[2] = cz;
+            }
+        }
         if (it == npoint - 1) break;  // the last pick needs no further update
 
         // ---- running-min update, reference rounding order, two points per instruction ----
@@ -173,8 +180,8 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
 }
 
 template <int P>
-static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, int C,
-                      cudaStream_t st) {
+static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, float *centres,
+                      int C, cudaStream_t st) {
     auto kern = fps_kernel<P>;
     const size_t smem = (size_t)3 * FPS_T * P * sizeof(float);
     B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -188,7 +195,7 @@ static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    B200PC_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, idx));
+    B200PC_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, idx, centres));
     return B200PC_OK;
 }
 
@@ -218,8 +225,8 @@ using namespace b200pc;
 
 extern "C" size_t b200pc_fps_workspace_bytes(int, int) { return 256; }
 
-extern "C" int b200pc_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, void *,
-                          size_t, b200pc_stream_t stream) {
+static int run_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, float *centres,
+                   b200pc_stream_t stream) {
     B200PC_REQUIRE(xyz && start && idx, "fps: null pointer");
     B200PC_REQUIRE(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
     B200PC_REQUIRE((long)N <= (long)FPS_MAX_CLUSTER * FPS_T * 16, "fps: N=%d exceeds the %d points one cluster can hold",
@@ -229,10 +236,21 @@ extern "C" int b200pc_fps(const float *xyz, int B, int N, int npoint, const int6
     fps_shape(B, N, &C, &P);
     cudaStream_t st = as_stream(stream);
     switch (P) {
-        case 1: return launch_fps<1>(xyz, B, N, npoint, start, idx, C, st);
-        case 2: return launch_fps<2>(xyz, B, N, npoint, start, idx, C, st);
-        case 4: return launch_fps<4>(xyz, B, N, npoint, start, idx, C, st);
-        case 8: return launch_fps<8>(xyz, B, N, npoint, start, idx, C, st);
-        default: return launch_fps<16>(xyz, B, N, npoint, start, idx, C, st);
+        case 1: return launch_fps<1>(xyz, B, N, npoint, start, idx, centres, C, st);
+        case 2: return launch_fps<2>(xyz, B, N, npoint, start, idx, centres, C, st);
+        case 4: return launch_fps<4>(xyz, B, N, npoint, start, idx, centres, C, st);
+        case 8: return launch_fps<8>(xyz, B, N, npoint, start, idx, centres, C, st);
+        default: return launch_fps<16>(xyz, B, N, npoint, start, idx, centres, C, st);
     }
+}
+
+extern "C" int b200pc_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, void *,
+                          size_t, b200pc_stream_t stream) {
+    return run_fps(xyz, B, N, npoint, start, idx, nullptr, stream);
+}
+
+extern "C" int b200pc_fps_sample(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx,
+                                 float *new_xyz, b200pc_stream_t stream) {
+    B200PC_REQUIRE(new_xyz, "fps_sample: null output pointer");
+    return run_fps(xyz, B, N, npoint, start, idx, new_xyz, stream);
 }

@@ -253,3 +253,18 @@ def test_poly_fit_rejects_cpu_and_bad_counts(cuda_dev):
     g = [x.to(cuda_dev) for x in f]
     with pytest.raises(ValueError):
         polypci.fit_and_predict(g, [[0.0, -1.0]], [0.5], 1)
+
+
+def test_sample_points_is_fps_plus_gather(cuda_dev):
+    # Sample.forward (Utils/Layers.py:23-27): the FPS kernel also writes the picks' coordinates
+    a, _ = synth.batch_pairs(60, 3, 16384)
+    for N, npoint in ((16384, 1024), (5000, 300), (700, 700)):
+        xyz = _t(a[:, :N], cuda_dev)
+        start = torch.tensor([5, 0, N - 1], dtype=torch.long)
+        idx, new_xyz = P.sample_points(xyz, npoint, start.to(cuda_dev))
+        np.testing.assert_array_equal(idx.cpu().numpy(), strict.farthest_point_sample(a[:, :N], npoint, start.numpy()))
+        assert torch.equal(new_xyz, P.index_points(xyz, idx))
+    torch.manual_seed(77)
+    i1, _ = P.sample_points(xyz, 64)
+    torch.manual_seed(77)
+    assert torch.equal(i1, P.farthest_point_sample(xyz, 64))           # same CPU-RNG draw as farthest_point_sample
