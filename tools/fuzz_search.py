@@ -15,7 +15,7 @@ def run(cases, seed, dev="cuda:0"):
   bad = 0
   old = os.environ.get("B200PC_SMALL_PATH")
   for c in range(cases):
-      B = int(rng.integers(1, 4)); N = int(rng.integers(1, 3000)); S = int(rng.integers(1, 1500))
+      B = int(rng.integers(1, 4)); N = int(rng.integers(1, int(os.environ.get("FUZZ_NMAX", "3000")))); S = int(rng.integers(1, int(os.environ.get("FUZZ_SMAX", "1500"))))
       scale = float(10.0 ** rng.uniform(-2, 2.5)); off = rng.normal(size=3) * scale * float(rng.choice([0, 0, 1, 20]))
       ref = (rng.normal(size=(B, N, 3)) * scale + off).astype(np.float32)
       qry = (rng.normal(size=(B, S, 3)) * scale + off).astype(np.float32)
