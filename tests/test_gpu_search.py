@@ -238,3 +238,20 @@ def test_randomised_shapes_scales_and_ties_fuzz(cuda_dev):
     spec = importlib.util.spec_from_file_location("fuzz_search", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_search.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
     assert mod.run(60, 11, cuda_dev) == 0
+
+
+@pytest.mark.parametrize("form", [0, 2])
+def test_knn_spatially_sorted_clouds_exact_and_not_pathological(cuda_dev, monkeypatch, form):
+    # a scan-ordered / spatially sorted cloud is the adversarial arrival order for a streaming k-best; the strided
+    # tiles (search.cu slot_to_ref) make it behave like a shuffled one.  Results are identical either way.
+    a, b = synth.batch_pairs(31, 2, 16384)
+    order = lambda x: np.stack([c[np.lexsort((c[:, 2], c[:, 1], np.round(c[:, 0])))] for c in x])     # sorted along x, then y
+    ref, qry = order(a), order(b)[:, ::8].copy()
+    r, q = _t(ref, cuda_dev), _t(qry, cuda_dev)
+    idx, dist = ops.knn_search(r, q, 16, form, want_dist=True)
+    oi, od = strict.knn(ref, qry, 16, form)
+    np.testing.assert_array_equal(_bits(dist.cpu().numpy()), _bits(od))
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    monkeypatch.setenv("B200PC_NATURAL_ORDER", "1")                       # refs visited in index order: same answer
+    idx2, dist2 = ops.knn_search(r, q, 16, form, want_dist=True)
+    assert torch.equal(idx, idx2) and torch.equal(dist, dist2)
