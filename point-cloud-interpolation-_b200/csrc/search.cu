@@ -497,11 +497,12 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                                 const int off = base + __ffs(cur) - 1;
                                 cur &= cur - 1;
                                 const float d = ref_dist<FORM>(tp, off, ex, ey, ez, nq);
-                                if (d <= tau[j]) {      // the refs are not visited in index order: an equal distance still wins
-                                    const unsigned long long key =       // with a lower index -- compare whole keys
-                                        ((unsigned long long)order_key(d) << 32) | (uint32_t)slot_to_ref(tile_ref0 + off, P.strided, P.n_pad / TILE);
-                                    if (key < lds_u64(hb)) {
-                                        heap_sift_root<true>(hb, SB, (uint32_t)k * SB, key);
+                                if (d <= tau[j]) {
+                                    // the refs are not visited in index order: an EQUAL distance still wins with a lower index
+                                    // than the root's (rare; only then is the root read)
+                                    const uint32_t ri = (uint32_t)slot_to_ref(tile_ref0 + off, P.strided, P.n_pad / TILE);
+                                    if (d < tau[j] || ri < (uint32_t)lds_u64(hb)) {
+                                        heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | ri);
                                         tau[j] = key_to_float((uint32_t)(lds_u64(hb) >> 32));
                                     }
                                 }
