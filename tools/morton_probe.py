@@ -29,6 +29,15 @@ print("random queries, random refs      : %.3f ms" % t(lambda: P.knn_point(16, r
 for cell in (1.0, 0.25):
     qs = torch.from_numpy(sort_rows(b, cell)).to(dev)
     print("Morton queries (cell %.2f m)     : %.3f ms" % (cell, t(lambda: P.knn_point(16, ref, qs))), flush=True)
+def cell_rows(x, cell):       # counting-sort order: row-major 2-D cells, arbitrary order inside a cell
+    out = np.empty_like(x)
+    for i in range(x.shape[0]):
+        cx = np.floor((x[i][:, 0] + 100.0) / cell).astype(np.int64); cy = np.floor((x[i][:, 1] + 100.0) / cell).astype(np.int64)
+        out[i] = x[i][np.argsort(cy * 4096 + cx, kind="stable")]
+    return out
+for cell in (8.0, 4.0, 2.0):
+    qc = torch.from_numpy(cell_rows(b, cell)).to(dev)
+    print("row-major %.0f m cells (queries)   : %.3f ms" % (cell, t(lambda: P.knn_point(16, ref, qc))), flush=True)
 rs = torch.from_numpy(sort_rows(a, 0.25)).to(dev)
 print("Morton queries + Morton refs     : %.3f ms" % t(lambda: P.knn_point(16, rs, qs)), flush=True)
 print("random queries + Morton refs     : %.3f ms" % t(lambda: P.knn_point(16, rs, qry)), flush=True)
