@@ -227,11 +227,11 @@ extern "C" size_t b200pc_fps_workspace_bytes(int, int) { return 256; }
 
 static int run_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, float *centres,
                    b200pc_stream_t stream) {
-    B200PC_REQUIRE(xyz && start && idx, "fps: null pointer");
     B200PC_REQUIRE(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
     B200PC_REQUIRE((long)N <= (long)FPS_MAX_CLUSTER * FPS_T * 16, "fps: N=%d exceeds the %d points one cluster can hold",
                    N, FPS_MAX_CLUSTER * FPS_T * 16);
     if (B == 0 || npoint == 0) return B200PC_OK;
+    B200PC_REQUIRE(xyz && start && idx, "fps: null pointer");
     int C, P;
     fps_shape(B, N, &C, &P);
     cudaStream_t st = as_stream(stream);
@@ -251,6 +251,6 @@ extern "C" int b200pc_fps(const float *xyz, int B, int N, int npoint, const int6
 
 extern "C" int b200pc_fps_sample(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx,
                                  float *new_xyz, b200pc_stream_t stream) {
-    B200PC_REQUIRE(new_xyz, "fps_sample: null output pointer");
+    B200PC_REQUIRE(new_xyz || B == 0 || npoint == 0, "fps_sample: null output pointer");
     return run_fps(xyz, B, N, npoint, start, idx, new_xyz, stream);
 }

@@ -286,9 +286,9 @@ using namespace b200pc;
 
 extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int N, int C, int64_t R, float *out,
                              int *oob_flag, b200pc_stream_t stream) {
-    B200PC_REQUIRE(points && idx && out, "gather: null pointer");
     B200PC_REQUIRE(B >= 0 && N >= 1 && C >= 1 && R >= 0, "gather: bad sizes");
     if (B == 0 || R == 0) return B200PC_OK;
+    B200PC_REQUIRE(points && idx && out, "gather: null pointer");
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
         const long rows = (long)B * R;
@@ -318,8 +318,8 @@ extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int
 
 extern "C" int b200pc_gather_bwd(const float *gout, const int64_t *idx, int B, int N, int C, int64_t R, float *gpoints,
                                  b200pc_stream_t stream) {
-    B200PC_REQUIRE(gout && idx && gpoints, "gather_bwd: null pointer");
     if (B == 0 || R == 0) return B200PC_OK;
+    B200PC_REQUIRE(gout && idx && gpoints, "gather_bwd: null pointer");
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(gout) && aligned16(gpoints)) {
         const long total = (long)B * R * (C / 4);
@@ -353,8 +353,8 @@ extern "C" int b200pc_three_nn(const float *unknown, const float *known, int B, 
 
 extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, const float *weight, int B, int S, int N,
                                         int C, float *out, b200pc_stream_t stream) {
-    B200PC_REQUIRE(feat && idx && weight && out, "three_interpolate: null pointer");
     if (B == 0 || N == 0) return B200PC_OK;
+    B200PC_REQUIRE(feat && idx && weight && out, "three_interpolate: null pointer");
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(feat) && aligned16(out) && (long)B * S * (C / 4) < (1L << 31)) {
         const long rows = (long)B * N;
@@ -380,8 +380,8 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
 extern "C" int b200pc_three_interpolate_bwd(const float *gout, const float *feat, const int64_t *idx, const float *weight,
                                             int B, int S, int N, int C, float *gfeat, float *gweight,
                                             b200pc_stream_t stream) {
-    B200PC_REQUIRE(gout && feat && idx && weight && gfeat, "three_interpolate_bwd: null pointer");
     if (B == 0 || N == 0) return B200PC_OK;
+    B200PC_REQUIRE(gout && feat && idx && weight && gfeat, "three_interpolate_bwd: null pointer");
     const long rows = (long)B * N;
     interp_bwd_kernel<<<wave_grid(rows * 32, 256, 1), 256, 0, as_stream(stream)>>>(gout, feat, idx, weight, S, C, (long)N,
                                                                                   rows, gfeat, gweight);

@@ -104,10 +104,10 @@ using namespace b200pc;
 
 extern "C" int b200pc_group_points(const float *xyz, const float *new_xyz, const float *feat, const int64_t *idx, int B,
                                    int N, int S, int K, int D, int xyz_first, float *out, b200pc_stream_t stream) {
-    B200PC_REQUIRE(xyz && new_xyz && idx && out, "group_points: null pointer");
     B200PC_REQUIRE(D == 0 || feat, "group_points: D=%d feature channels but no feature pointer", D);
     B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && K >= 0 && D >= 0, "group_points: bad sizes B=%d N=%d S=%d K=%d D=%d", B, N, S, K, D);
     if (B == 0 || S == 0 || K == 0) return B200PC_OK;
+    B200PC_REQUIRE(xyz && new_xyz && idx && out, "group_points: null pointer");
     const long total = (long)B * K * S;
     B200PC_REQUIRE((total + 255) / 256 < (1L << 31), "group_points: problem too large for one launch");
     const unsigned blocks = (unsigned)((total + 255) / 256);
@@ -123,10 +123,10 @@ extern "C" int b200pc_group_points(const float *xyz, const float *new_xyz, const
 
 extern "C" int b200pc_group_points_bwd(const float *grad_out, const int64_t *idx, int B, int N, int S, int K, int D,
                                        int xyz_first, float *grad_feat, b200pc_stream_t stream) {
-    B200PC_REQUIRE(grad_out && idx && grad_feat, "group_points_bwd: null pointer");
     B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && K >= 0 && D >= 1, "group_points_bwd: bad sizes");
     B200PC_REQUIRE(K <= 65535 && B <= 65535, "group_points_bwd: K=%d / B=%d exceed the grid limits", K, B);
     if (B == 0 || S == 0 || K == 0) return B200PC_OK;
+    B200PC_REQUIRE(grad_out && idx && grad_feat, "group_points_bwd: null pointer");
     dim3 grid((S + GROUP_S - 1) / GROUP_S, K, B);
     group_points_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad_out, idx, N, S, K, D, xyz_first != 0, grad_feat);
     B200PC_LAUNCH_CHECK();

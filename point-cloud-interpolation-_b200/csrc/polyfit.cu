@@ -44,11 +44,11 @@ using namespace b200pc;
 
 extern "C" int b200pc_poly_predict(const float *const *frames, const double *weights, int B, int F, int64_t per_batch, float *out,
                                    b200pc_stream_t stream) {
-    B200PC_REQUIRE(frames && weights && out, "poly_predict: null pointer");
     B200PC_REQUIRE(F >= 1 && F <= POLY_MAX_FRAMES, "poly_predict: F=%d frames, supported 1..%d", F, POLY_MAX_FRAMES);
     B200PC_REQUIRE(B >= 0 && per_batch >= 0, "poly_predict: bad sizes");
     const long total = (long)B * per_batch;
     if (total == 0) return B200PC_OK;
+    B200PC_REQUIRE(frames && weights && out, "poly_predict: null pointer");
     FramePtrs fp;
     for (int f = 0; f < POLY_MAX_FRAMES; ++f) fp.p[f] = f < F ? frames[f] : nullptr;
     for (int f = 0; f < F; ++f) B200PC_REQUIRE(fp.p[f], "poly_predict: frame %d is null", f);

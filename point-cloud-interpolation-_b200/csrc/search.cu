@@ -766,10 +766,10 @@ static int launch_shape(const SearchArgs &a, const SearchPlan &pl, int B, cudaSt
 
 static int run_search(const float *ref, const float *qry, int B, int N, int S, int k, int form, int mode, float r2,
                       int64_t *idx, float *dist, void *ws, size_t ws_bytes, cudaStream_t st) {
-    B200PC_REQUIRE(ref && qry, "search: null input pointer");
     B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && k >= 1, "search: bad sizes B=%d N=%d S=%d k=%d", B, N, S, k);
+    if (B == 0 || S == 0) return B200PC_OK;             // empty work: nothing to validate, empty tensors have null pointers
     B200PC_REQUIRE(idx || dist, "search: no output requested");
-    if (B == 0 || S == 0) return B200PC_OK;
+    B200PC_REQUIRE(ref && qry, "search: null input pointer");
     {   // small reference sets: warp-per-query kernel, one launch, no workspace (small_search.cu)
         const int rc_small = run_small(ref, qry, B, N, S, k, form, mode, r2, idx, dist, st);
         if (rc_small != -100) return rc_small;
@@ -835,7 +835,7 @@ int run_topk(const float *ref, const float *qry, int B, int N, int S, int k, int
 
 int run_ball(const float *ref, const float *qry, int B, int N, int S, float r2, int nsample, int64_t *idx,
              void *ws, size_t ws_bytes, cudaStream_t st) {
-    B200PC_REQUIRE(idx, "ball_query: null output pointer");
+    B200PC_REQUIRE(idx || B == 0 || S == 0, "ball_query: null output pointer");
     return run_search(ref, qry, B, N, S, nsample, B200PC_FORM_QRY_NORM_FIRST, MODE_BALL, r2, idx, nullptr, ws,
                       ws_bytes, st);
 }

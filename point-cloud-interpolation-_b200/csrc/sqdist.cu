@@ -74,9 +74,9 @@ using namespace b200pc;
 
 extern "C" int b200pc_square_distance(const float *src, const float *dst, int B, int N, int M, float *out,
                                       b200pc_stream_t stream) {
-    B200PC_REQUIRE(src && dst && out, "square_distance: null pointer");
     B200PC_REQUIRE(B >= 0 && N >= 0 && M >= 0, "square_distance: bad sizes");
     if (B == 0 || N == 0 || M == 0) return B200PC_OK;
+    B200PC_REQUIRE(src && dst && out, "square_distance: null pointer");
     const int vec_ok = (M % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     dim3 grid((M + SQD_THREADS * 4 - 1) / (SQD_THREADS * 4), (N + SQD_ROWS - 1) / SQD_ROWS, B);
     B200PC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "square_distance: problem too large for one launch");

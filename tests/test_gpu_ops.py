@@ -268,3 +268,21 @@ def test_sample_points_is_fps_plus_gather(cuda_dev):
     i1, _ = P.sample_points(xyz, 64)
     torch.manual_seed(77)
     assert torch.equal(i1, P.farthest_point_sample(xyz, 64))           # same CPU-RNG draw as farthest_point_sample
+
+
+def test_empty_work_is_accepted_everywhere(cuda_dev):
+    # zero queries / clouds / samples / neighbours: empty tensors (null data pointers) in, empty tensors out, like torch
+    from b200pc import pytorch3d_shim as S3
+    x = torch.randn(2, 100, 3, device=cuda_dev)
+    z = lambda *s: torch.zeros(*s, dtype=torch.long, device=cuda_dev)
+    assert P.knn_point(4, x, x[:, :0]).shape == (2, 0, 4)
+    assert P.knn_point(4, x[:0], x[:0, :10]).shape == (0, 10, 4)
+    assert P.query_ball_point(1.0, 4, x, x[:, :0]).shape == (2, 0, 4)
+    assert ops.fps(x, 0, z(2)).shape == (2, 0)
+    assert P.index_points(x, z(2, 0)).shape == (2, 0, 3)
+    assert P.group_points(x, x[:, :5].contiguous(), None, z(2, 5, 0)).shape == (2, 3, 0, 5)
+    assert P.group_points(x, x[:, :0].contiguous(), None, z(2, 0, 3)).shape == (2, 3, 3, 0)
+    assert S3.knn_points(x, x, K=0).idx.shape == (2, 100, 0)
+    assert P.three_interpolate(torch.randn(2, 10, 8, device=cuda_dev), z(2, 0, 3), torch.zeros(2, 0, 3, device=cuda_dev)).shape == (2, 0, 8)
+    assert P.knn_point(1, x[:, :1].contiguous(), x).eq(0).all()                      # a single reference point
+    torch.cuda.synchronize()
