@@ -768,8 +768,8 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
                       int64_t *idx, float *dist, void *ws, size_t ws_bytes, cudaStream_t st) {
     B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && k >= 1, "search: bad sizes B=%d N=%d S=%d k=%d", B, N, S, k);
     if (B == 0 || S == 0) return B200PC_OK;             // empty work: nothing to validate, empty tensors have null pointers
-    B200PC_REQUIRE(idx || dist, "search: no output requested");
     B200PC_REQUIRE(ref && qry, "search: null input pointer");
+    B200PC_REQUIRE(idx || dist, "search: no output requested");
     {   // small reference sets: warp-per-query kernel, one launch, no workspace (small_search.cu)
         const int rc_small = run_small(ref, qry, B, N, S, k, form, mode, r2, idx, dist, st);
         if (rc_small != -100) return rc_small;
