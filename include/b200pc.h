@@ -63,7 +63,9 @@ int b200pc_square_distance(const float *src, const float *dst, int B, int N, int
 /* form 0  -> Group.forward kNN branch, Utils/Layers.py:50-53 (exposed as knn_point)
  * form 2  -> pytorch3d.ops.knn_points(p1=qry, p2=ref, K=k) as called at Utils/Layers.py:220,
  *            311,393,430; PolyPCI/Models/Models_V1.py:113; PointINet20230424/models/layers.py:360
- * idx [B,S,k] int64 ascending by (distance, index); dist [B,S,k] may be NULL.               */
+ * idx [B,S,k] int64 ascending by (distance, index); dist [B,S,k] may be NULL.
+ * k <= N (EINVAL otherwise, like torch.topk); the k-best lists live in shared memory: k up to ~780.  Empty work
+ * (B == 0 or S == 0) returns OK without looking at the pointers.                                       */
 int b200pc_knn(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
                float *dist, void *workspace, size_t workspace_bytes, b200pc_stream_t stream);
 
