@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                 float *dout = P.dist_out ? P.dist_out + row * k : nullptr;
                 for (int e = 0; e < k; ++e) {
                     const unsigned long long key = heap_all[e * QPB + slot];
-                    if (io) io[e] = (int64_t)(uint32_t)key;
+                    if (io) io[e] = (int64_t)(int32_t)(uint32_t)key;     // unfilled slot (a NaN query ranks nothing): -1, distance +inf
                     if (dout) dout[e] = key_to_float((uint32_t)(key >> 32));
                 }
             } else {
