@@ -149,11 +149,12 @@ static void select_k(const float *row, int n, int k, float *scratch, int64_t *id
     float tau = kth_smallest(scratch, n, k - 1);
     int cnt = 0;
     /* strictly below the threshold: all of them belong */
-    for (int i = 0; i < n; i++)
+    for (int i = 0; i < n && cnt < k; i++)   /* the bound only matters for NaN rows (no order): stay inside the buffers */
         if (row[i] < tau) { idx_out[cnt] = i; val_out[cnt] = row[i]; cnt++; }
     /* equal to the threshold: lowest indices first until k are collected */
     for (int i = 0; i < n && cnt < k; i++)
         if (row[i] == tau) { idx_out[cnt] = i; val_out[cnt] = row[i]; cnt++; }
+    for (; cnt < k; cnt++) { idx_out[cnt] = -1; val_out[cnt] = INFINITY; }   /* NaN rows only */
     /* order the k survivors by (value, index) */
     for (int a = 1; a < k; a++) {
         float v = val_out[a]; int64_t id = idx_out[a]; int b = a - 1;
