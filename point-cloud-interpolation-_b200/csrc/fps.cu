@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
         mbar_fence_init();
     }
     int far = (int)start[b];
+    far = far < 0 ? 0 : (far >= N ? N - 1 : far);      // a bad start index must not read outside the cloud
     float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
     if (C > 1) cluster.sync(); else __syncthreads();
 
