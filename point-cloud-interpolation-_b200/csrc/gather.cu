@@ -150,6 +150,13 @@ __global__ void three_weights_kernel(const float *__restrict__ dist, long rows, 
 // ------------------------------------------------------------------------------------------
 // three_interpolate: out[b,n,:] = (f[i0]*w0 + f[i1]*w1) + f[i2]*w2   (separate mul / add)
 // ------------------------------------------------------------------------------------------
+// index hygiene of the interpolation kernels: negative indices wrap once (torch indexing); an index that is still out
+// of range contributes nothing (row 0 with weight 0) instead of reading outside the table -- the reference raises there.
+__device__ __forceinline__ void clean_neighbour(long &i, float &w, int S) {
+    if (i < 0) i += S;
+    if (i < 0 || i >= S) { i = 0; w = 0.0f; }
+}
+
 __device__ __forceinline__ float mix3(float a, float wa, float b, float wb, float c, float wc) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb)), __fmul_rn(c, wc));
 }
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(256, 3) interp_rows_kernel(const float4 *__res
     float w_next = 0.f;
     {
         const long row = warp * ROWS + lane / 3;
-        if (lane < 3 * ROWS && row < rows_total) { i_next = idx[row * 3 + lane % 3]; w_next = w[row * 3 + lane % 3]; }
+        if (lane < 3 * ROWS && row < rows_total) { i_next = idx[row * 3 + lane % 3]; w_next = w[row * 3 + lane % 3]; clean_neighbour(i_next, w_next, S); }
     }
     for (long r0 = warp * ROWS; r0 < rows_total; r0 += nwarps * ROWS) {
         int src = 0;
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(256, 3) interp_rows_kernel(const float4 *__res
         const long i_cur = i_next;
         {
             const long rn = r0 + nwarps * ROWS + lane / 3;
-            if (lane < 3 * ROWS && rn < rows_total) { i_next = idx[rn * 3 + lane % 3]; w_next = w[rn * 3 + lane % 3]; }
+            if (lane < 3 * ROWS && rn < rows_total) { i_next = idx[rn * 3 + lane % 3]; w_next = w[rn * 3 + lane % 3]; clean_neighbour(i_next, w_next, S); }
         }
         if (lane < 3 * ROWS) {                          // lane = 3*u + j  ->  neighbour j of row r0+u
             const long row = r0 + lane / 3;
@@ -222,8 +229,9 @@ __global__ void __launch_bounds__(256) interp_flat_kernel(const float4 *__restri
     const long row = t / C4;
     const int col = (int)(t - row * C4);
     const long base = (row / N) * S;
-    const long i0 = __ldg(idx + row * 3), i1 = __ldg(idx + row * 3 + 1), i2 = __ldg(idx + row * 3 + 2);
-    const float w0 = __ldg(w + row * 3), w1 = __ldg(w + row * 3 + 1), w2 = __ldg(w + row * 3 + 2);
+    long i0 = __ldg(idx + row * 3), i1 = __ldg(idx + row * 3 + 1), i2 = __ldg(idx + row * 3 + 2);
+    float w0 = __ldg(w + row * 3), w1 = __ldg(w + row * 3 + 1), w2 = __ldg(w + row * 3 + 2);
+    clean_neighbour(i0, w0, S); clean_neighbour(i1, w1, S); clean_neighbour(i2, w2, S);
     const float4 a = __ldg(feat + (base + i0) * C4 + col), b = __ldg(feat + (base + i1) * C4 + col), c = __ldg(feat + (base + i2) * C4 + col);
     float4 o;
     o.x = mix3(a.x, w0, b.x, w1, c.x, w2); o.y = mix3(a.y, w0, b.y, w1, c.y, w2);
@@ -239,9 +247,11 @@ __global__ void __launch_bounds__(256) interp_scalar_kernel(const float *__restr
         const long row = v / C;
         const int col = (int)(v - row * C);
         const long b = row / N;
-        const long i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
-        out[v] = mix3(__ldg(feat + (b * S + i0) * C + col), w[row * 3], __ldg(feat + (b * S + i1) * C + col), w[row * 3 + 1],
-                      __ldg(feat + (b * S + i2) * C + col), w[row * 3 + 2]);
+        long i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
+        float w0 = w[row * 3], w1 = w[row * 3 + 1], w2 = w[row * 3 + 2];
+        clean_neighbour(i0, w0, S); clean_neighbour(i1, w1, S); clean_neighbour(i2, w2, S);
+        out[v] = mix3(__ldg(feat + (b * S + i0) * C + col), w0, __ldg(feat + (b * S + i1) * C + col), w1,
+                      __ldg(feat + (b * S + i2) * C + col), w2);
     }
 }
 
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(const float *__restrict
         long id[3];
         float ww[3], acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { id[j] = idx[row * 3 + j]; ww[j] = w[row * 3 + j]; }
+        for (int j = 0; j < 3; ++j) { id[j] = idx[row * 3 + j]; ww[j] = w[row * 3 + j]; clean_neighbour(id[j], ww[j], S); }
         for (int c = lane; c < C; c += 32) {
             const float g = gout[row * C + c];
 #pragma unroll

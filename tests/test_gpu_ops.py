@@ -286,3 +286,15 @@ def test_empty_work_is_accepted_everywhere(cuda_dev):
     assert P.three_interpolate(torch.randn(2, 10, 8, device=cuda_dev), z(2, 0, 3), torch.zeros(2, 0, 3, device=cuda_dev)).shape == (2, 0, 8)
     assert P.knn_point(1, x[:, :1].contiguous(), x).eq(0).all()                      # a single reference point
     torch.cuda.synchronize()
+
+
+def test_three_interpolate_index_hygiene(cuda_dev):
+    # negative indices wrap once like torch indexing; an index that is still out of range contributes nothing
+    feat = torch.randn(1, 10, 8, device=cuda_dev)
+    idx = torch.tensor([[[0, 1, 2], [-1, -10, 9], [3, 10, 4], [5, -11, 6]]], device=cuda_dev)
+    w = torch.tensor([[[0.2, 0.3, 0.5]] * 4], device=cuda_dev)
+    out = P.three_interpolate(feat, idx, w)
+    f = feat[0]
+    want = torch.stack([0.2 * f[0] + 0.3 * f[1] + 0.5 * f[2], 0.2 * f[9] + 0.3 * f[0] + 0.5 * f[9],
+                        0.2 * f[3] + 0.5 * f[4], 0.2 * f[5] + 0.5 * f[6]])[None]
+    torch.testing.assert_close(out, want, rtol=1e-6, atol=1e-6)
