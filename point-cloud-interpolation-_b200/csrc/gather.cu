@@ -153,8 +153,10 @@ __global__ void three_weights_kernel(const float *__restrict__ dist, long rows, 
 // index hygiene of the interpolation kernels: negative indices wrap once (torch indexing); an index that is still out
 // of range contributes nothing (row 0 with weight 0) instead of reading outside the table -- the reference raises there.
 __device__ __forceinline__ void clean_neighbour(long &i, float &w, int S) {
-    if (i < 0) i += S;
-    if (i < 0 || i >= S) { i = 0; w = 0.0f; }
+    if ((unsigned long long)i >= (unsigned long long)S) {      // one compare on the common path
+        if (i < 0) i += S;
+        if (i < 0 || i >= S) { i = 0; w = 0.0f; }
+    }
 }
 
 __device__ __forceinline__ float mix3(float a, float wa, float b, float wb, float c, float wc) {
@@ -177,15 +179,16 @@ __global__ void __launch_bounds__(256, 3) interp_rows_kernel(const float4 *__res
     float w_next = 0.f;
     {
         const long row = warp * ROWS + lane / 3;
-        if (lane < 3 * ROWS && row < rows_total) { i_next = idx[row * 3 + lane % 3]; w_next = w[row * 3 + lane % 3]; clean_neighbour(i_next, w_next, S); }
+        if (lane < 3 * ROWS && row < rows_total) { i_next = idx[row * 3 + lane % 3]; w_next = w[row * 3 + lane % 3]; }
     }
     for (long r0 = warp * ROWS; r0 < rows_total; r0 += nwarps * ROWS) {
         int src = 0;
-        const float wt = w_next;
-        const long i_cur = i_next;
+        float wt = w_next;
+        long i_cur = i_next;
+        clean_neighbour(i_cur, wt, S);                   // at the point of use: the prefetch below stays in flight
         {
             const long rn = r0 + nwarps * ROWS + lane / 3;
-            if (lane < 3 * ROWS && rn < rows_total) { i_next = idx[rn * 3 + lane % 3]; w_next = w[rn * 3 + lane % 3]; clean_neighbour(i_next, w_next, S); }
+            if (lane < 3 * ROWS && rn < rows_total) { i_next = idx[rn * 3 + lane % 3]; w_next = w[rn * 3 + lane % 3]; }
         }
         if (lane < 3 * ROWS) {                          // lane = 3*u + j  ->  neighbour j of row r0+u
             const long row = r0 + lane / 3;
