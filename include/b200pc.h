@@ -99,8 +99,8 @@ int b200pc_three_interpolate_bwd(const float *gout, const float *feat, const int
 int b200pc_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, void *workspace,
                size_t workspace_bytes, b200pc_stream_t stream);
 
-/* a7: Sample.forward (Utils/Layers.py:23-27) = farthest_point_sample + index_points(points, ind): the same kernel also
- * writes the coordinates of every pick, new_xyz [B,npoint,3] (bit-identical to gathering xyz with idx afterwards).   */
+/* a7: Sample.forward (Utils/Layers.py:23-27) = farthest_point_sample + index_points(points, ind) behind one call:
+ * idx [B,npoint] and the picks' coordinates new_xyz [B,npoint,3] (the FPS kernel followed by the gather kernel).     */
 int b200pc_fps_sample(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, float *new_xyz,
                       b200pc_stream_t stream);
 

@@ -110,7 +110,7 @@ def ball_query(radius, nsample, xyz, new_xyz):
 
 def fps(xyz, npoint, start, want_xyz=False):
     """Utils/Pointnet2Utils.py:64  start [B] int64 (first centroid) -> [B,npoint] int64.
-    want_xyz: also return the picks' coordinates [B,npoint,3] from the same kernel (Sample.forward, Utils/Layers.py:23-27)."""
+    want_xyz: also return the picks' coordinates [B,npoint,3] from the same C call (Sample.forward, Utils/Layers.py:23-27)."""
     xyz = _prep(xyz, "xyz")
     B, N, _ = xyz.shape
     dev = xyz.device

@@ -160,7 +160,7 @@ class SetConv(nn.Module):
         rows = _rows(xyz)
         sample = getattr(self.be, "sample_points", None)
         if sample is not None:
-            _, centre_rows = sample(rows, self.npoint)                                                 # FPS + gather in one kernel
+            _, centre_rows = sample(rows, self.npoint)                                                 # FPS + gather behind one call
         else:
             centre_rows = self.be.index_points(rows, self.be.farthest_point_sample(rows, self.npoint))     # [B,S,3]
         centres = _rows(centre_rows)

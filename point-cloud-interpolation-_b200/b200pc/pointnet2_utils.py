@@ -40,7 +40,7 @@ def farthest_point_sample(xyz, npoint):
 
 def sample_points(xyz, npoint, start=None):
     """Sample.forward (Utils/Layers.py:23-27) on point-major input: farthest_point_sample + index_points(points, ind) in
-    one kernel.  xyz [B,N,3] -> (idx [B,npoint] int64, new_xyz [B,npoint,3]).  The start index is drawn exactly like
+    one C call.  xyz [B,N,3] -> (idx [B,npoint] int64, new_xyz [B,npoint,3]).  The start index is drawn exactly like
     farthest_point_sample does unless `start` [B] is given."""
     if start is None:
         start = torch.randint(0, xyz.shape[1], (xyz.shape[0],), dtype=torch.long).to(xyz.device, non_blocking=True)

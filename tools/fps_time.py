@@ -16,4 +16,5 @@ def t(fn, n=5):
 for B, N, npt in ((1, 16384, 1024), (16, 16384, 4096), (1, 1024, 256), (1, 256, 64), (2, 16384, 1024), (1, 8192, 2048), (8, 4096, 1024)):
     x = xyz16[:B, :N].contiguous(); st = torch.zeros(B, dtype=torch.long, device=dev)
     ms = t(lambda: ops.fps(x, npt, st))
-    print("FPS B=%2d N=%5d -> %4d : %.3f ms  %.3f us/round" % (B, N, npt, ms, ms * 1e3 / npt), flush=True)
+    ms2 = t(lambda: ops.fps(x, npt, st, want_xyz=True))
+    print("FPS B=%2d N=%5d -> %4d : %.3f ms  %.3f us/round   (+coordinates: %.3f ms)" % (B, N, npt, ms, ms * 1e3 / npt, ms2), flush=True)
