@@ -26,12 +26,17 @@ def _streams(device, n):
     return _STREAMS[key]
 
 
+def plan_chunks(B, S, chunks="auto"):
+    """how many batch chunks a host-buffer search is split into: "auto" = one chunk per resident wave of queries."""
+    if chunks == "auto":
+        chunks = (B * S) // _WAVE_QUERIES
+    return max(1, min(int(chunks), max(B, 1)))
+
+
 def _pipelined(op, host_inputs, host_out, device, chunks):
     device = torch.device(device)
     B = host_inputs[0].shape[0]
-    if chunks == "auto":
-        chunks = (B * host_inputs[-1].shape[1]) // _WAVE_QUERIES      # host_inputs[-1] = the queries [B,S,3]
-    chunks = max(1, min(int(chunks), B))
+    chunks = plan_chunks(B, host_inputs[-1].shape[1], chunks)         # host_inputs[-1] = the queries [B,S,3]
     bounds = [(i * B // chunks, (i + 1) * B // chunks) for i in range(chunks)]
     streams = _streams(device, 2)
     cur = torch.cuda.current_stream(device)

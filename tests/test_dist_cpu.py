@@ -69,3 +69,14 @@ def test_bench_reference_arm_under_torchrun_world2():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "knn_point_gqueries_per_s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_hostio_chunk_plan():
+    # C2 (8 x 16384 queries) is exactly one resident wave of the search kernel: not split; bigger batches are
+    from b200pc import hostio
+    assert hostio.plan_chunks(8, 16384) == 1
+    assert hostio.plan_chunks(32, 16384) == 3
+    assert hostio.plan_chunks(64, 16384) == 7
+    assert hostio.plan_chunks(2, 1024) == 1
+    assert hostio.plan_chunks(8, 16384, chunks=4) == 4 and hostio.plan_chunks(2, 16384, chunks=5) == 2
+    assert hostio.plan_chunks(0, 0) == 1
