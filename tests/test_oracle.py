@@ -270,3 +270,34 @@ def test_golden_polyfit_restatement_and_linear_weights():
         assert w.shape == (len(T),) and w.dtype == np.float64
         np.testing.assert_allclose((w @ frames.astype(np.float64)).astype(np.float32)[None], gold, rtol=2e-6, atol=1e-6)
         assert abs(w.sum() - 1.0) < 1e-12                                 # a polynomial fit reproduces constants
+
+
+# ---------------------------------------------------------------- the search kernel's conservative prefilter, emulated
+def _fma32(a, b, c):
+    # one rounding: the product of two fp32 is exact in fp64; the sum is rounded to fp32 once for all but ~2^-29 of the cases
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+@pytest.mark.parametrize("scale,offset", [(30.0, 0.0), (1.0, 0.0), (30.0, 2000.0), (1e-3, 0.0), (5.0, 3e5)])
+def test_filter_threshold_is_conservative_for_all_three_forms(scale, offset):
+    """search.cu: u = fma(z,-2qz, fma(y,-2qy, fma(x,-2qx, w'))) with w' = |r|^2 (1 - 20 eps) must satisfy
+    dist_ref <= tau  =>  u < (tau - |q|^2) + 4.5e-7 |tau| + 1.1e-6 |q|^2 + 1e-35   for every reference rounding.
+    Checked with tau = the pair's own distance (the tightest threshold that must still let the pair through)."""
+    f32 = np.float32
+    rng = np.random.default_rng(int(scale * 7 + offset) % 1000)
+    n = 200000
+    r = (rng.normal(size=(n, 3)) * scale + offset).astype(f32)
+    q = (r + rng.normal(size=(n, 3)) * scale * rng.choice([1e-3, 1e-2, 0.1, 1.0], size=(n, 1))).astype(f32)
+    sqn = lambda p: ((p[:, 0] * p[:, 0]).astype(f32) + (p[:, 1] * p[:, 1]).astype(f32)).astype(f32) + (p[:, 2] * p[:, 2]).astype(f32)
+    w, nq = sqn(r).astype(f32), sqn(q).astype(f32)
+    a = (f32(-2.0) * q).astype(f32)
+    T = _fma32(r[:, 2], a[:, 2], _fma32(r[:, 1], a[:, 1], (r[:, 0] * a[:, 0]).astype(f32)))
+    d = {0: ((T + w).astype(f32) + nq).astype(f32), 1: ((T + nq).astype(f32) + w).astype(f32)}
+    dx, dy, dz = (q[:, 0] - r[:, 0]).astype(f32), (q[:, 1] - r[:, 1]).astype(f32), (q[:, 2] - r[:, 2]).astype(f32)
+    d[2] = _fma32(dz, dz, _fma32(dy, dy, (dx * dx).astype(f32)))
+    wp = (w * f32(1.0 - 20.0 * 5.9604645e-8)).astype(f32)
+    u = _fma32(r[:, 2], a[:, 2], _fma32(r[:, 1], a[:, 1], _fma32(r[:, 0], a[:, 0], wp)))
+    for form, tau in d.items():
+        margin = ((f32(4.5e-7) * np.abs(tau)).astype(f32) + ((f32(1.1e-6) * nq).astype(f32) + f32(1e-35)).astype(f32)).astype(f32)
+        thr = ((tau - nq).astype(f32) + margin).astype(f32)
+        assert (u < thr).all(), "form %d: %d of %d pairs would be filtered out" % (form, int((~(u < thr)).sum()), n)
