@@ -6,7 +6,7 @@
 //   * every thread keeps P points (x,y,z,min-dist) in REGISTERS for all rounds; 512 threads x
 //     P<=16 = 8192 points per CTA, up to 16 CTAs per cluster (131072 points);
 //   * the update is packed fp32x2 math in the reference's exact rounding order
-//     d = ((dx*dx + dy*dy) + dz*dz), dx = x - cx, no FMA;
+//     d = ((dx*dx + dy*dy) + dz*dz), dx = x - cx, every product rounded on its own;
 //   * arg-max: min-dists are >= +0, so their bit patterns order like unsigned ints:
 //     the pair (bits, ~index) is reduced as one key: two REDUX per warp, ONE __syncthreads per round,
 //     two REDUX over the warp keys (lowest index wins ties);
@@ -96,9 +96,14 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
                 const f32x2 dx = add2(pack2(x[p], x[p + 1]), ncx);
                 const f32x2 dy = add2(pack2(y[p], y[p + 1]), ncy);
                 const f32x2 dz = add2(pack2(z[p], z[p + 1]), ncz);
-                const f32x2 s = add2(add2(mul2(dx, dx), mul2(dy, dy)), mul2(dz, dz));
-                float d0, d1;
-                unpack2(s, d0, d1);
+                // Only the subtractions stay packed.  ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 (it even
+                // folds fma(d, d, -0.0) back to a product first), which would turn the reference's (dx*dx + dy*dy) + dz*dz into
+                // fma(dz,dz,fma(dy,dy,dx*dx)) and flip near-tied arg-max picks.  The scalar .rn intrinsics are never
+                // contracted (tests/test_abi.py checks the SASS of every fps_kernel: no FFMA2, no FMUL2, no FFMA).
+                float ax, bx, ay, by, az, bz;
+                unpack2(dx, ax, bx); unpack2(dy, ay, by); unpack2(dz, az, bz);
+                const float d0 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+                const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz));
                 mind[p] = fminf(mind[p], d0);
                 mind[p + 1] = fminf(mind[p + 1], d1);
                 lmax = fmaxf(lmax, fmaxf(mind[p], mind[p + 1]));

@@ -49,6 +49,32 @@ def test_hot_loop_uses_packed_fp32_and_bulk_tma():
         assert mnemonic in sass, "expected %s in the SASS of libb200pc.so" % mnemonic
 
 
+def _sass_by_function():
+    sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
+    out, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            out[name] = []
+        elif name is not None:
+            out[name].append(line)
+    return out
+
+
+def test_fps_kernels_never_fuse_multiply_add():
+    """farthest_point_sample computes (dx*dx + dy*dy) + dz*dz with every product rounded on its own
+    (Utils/Pointnet2Utils.py:80).  ptxas 12.9 contracts packed mul+add into FFMA2, so the kernel spells the
+    products with scalar .rn intrinsics; any fused multiply-add in its SASS would flip near-tied picks."""
+    funcs = {n: b for n, b in _sass_by_function().items() if "fps_kernel" in n}
+    assert len(funcs) == 5, sorted(funcs)
+    for name, body in funcs.items():
+        text = "\n".join(body)
+        for bad in ("FFMA2", "FMUL2", " FFMA ", "FFMA.", "DFMA"):
+            assert bad not in text, "%s contains %s" % (name, bad.strip())
+        assert " FMUL " in text and " FADD " in text
+
+
 def test_version_and_workspace_queries_need_no_gpu():
     lib = _lib.load()
     assert lib.b200pc_version() >= 100

@@ -56,6 +56,20 @@ def test_fps_duplicates_first_argmax(cuda_dev):
     np.testing.assert_array_equal(out.cpu().numpy(), strict.farthest_point_sample(dup, 2500, start))
 
 
+@pytest.mark.parametrize("N", [301, 1025, 2049, 4097, 8193, 16385, 40001])     # P = 1, 2, 4, 8, 16 and clusters of 2..8 CTAs
+def test_fps_near_ties_no_fused_multiply_add(cuda_dev, N):
+    """clouds built so that fma(dz,dz,fma(dy,dy,dx*dx)) picks a different point than the reference's
+    (dx*dx + dy*dy) + dz*dz already in the first round (tests/adversarial.py)"""
+    from adversarial import fps_rot90_cloud, first_round_pick
+    clouds = np.stack([fps_rot90_cloud(900 + i, N // 2) for i in range(4)])
+    for c in clouds:
+        assert first_round_pick(c, False) != first_round_pick(c, True)
+    start = np.zeros(4, np.int64)
+    npoint = min(64, N)
+    out = P.farthest_point_sample_from(_t(clouds, cuda_dev), npoint, _t(start, cuda_dev))
+    np.testing.assert_array_equal(out.cpu().numpy(), strict.farthest_point_sample(clouds, npoint, start))
+
+
 def test_fps_consumes_cpu_rng_like_reference(cuda_dev):
     a, _ = synth.batch_pairs(72, 2, 1024)
     torch.manual_seed(123)

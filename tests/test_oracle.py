@@ -301,3 +301,17 @@ def test_filter_threshold_is_conservative_for_all_three_forms(scale, offset):
         margin = ((f32(4.5e-7) * np.abs(tau)).astype(f32) + ((f32(1.1e-6) * nq).astype(f32) + f32(1e-35)).astype(f32)).astype(f32)
         thr = ((tau - nq).astype(f32) + margin).astype(f32)
         assert (u < thr).all(), "form %d: %d of %d pairs would be filtered out" % (form, int((~(u < thr)).sum()), n)
+
+
+def test_fps_oracle_is_unfused_on_the_near_tie_clouds():
+    """the adversarial FPS clouds: the oracle follows the unfused arithmetic (the reference's), which differs
+    from the fused one on every such cloud -- so the GPU test on the same data detects a contracted kernel"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from adversarial import fps_rot90_cloud, first_round_pick
+    for N in (301, 4097, 16385):
+        c = fps_rot90_cloud(900, N // 2)
+        a, b = first_round_pick(c, False), first_round_pick(c, True)
+        assert a != b
+        got = strict.farthest_point_sample(c[None], 2, np.array([0]))[0, 1]
+        assert got == a
