@@ -93,6 +93,15 @@ int b200pc_three_interpolate_bwd(const float *gout, const float *feat, const int
                                  int B, int S, int N, int C, float *gfeat, float *gweight,
                                  b200pc_stream_t stream);
 
+/* a5 in ONE call: three-NN search -> inverse-distance weights -> mix (FeaturePropagation.forward Utils/Layers.py:180-188,
+ * PointNetFeaturePropagation.forward Utils/Pointnet2Utils.py:297-304).  unknown [B,N,3], known [B,S,3], feat [B,S,C]
+ * -> out [B,N,C]; idx [B,N,3] and weight [B,N,3] are returned for the backward pass (b200pc_three_interpolate_bwd);
+ * the distances stay in the workspace.                                                         */
+size_t b200pc_feature_propagation_workspace_bytes(int B, int N, int S);
+int b200pc_feature_propagation(const float *unknown, const float *known, const float *feat, int B, int N, int S, int C,
+                               int variant, float *out, int64_t *idx, float *weight, void *workspace,
+                               size_t workspace_bytes, b200pc_stream_t stream);
+
 /* ---- a3: farthest_point_sample(xyz, npoint)  Utils/Pointnet2Utils.py:64-85 --------------- */
 /* start [B] int64: the first centroid of each cloud (the facade draws it with torch.randint
  * on the CPU generator exactly as the reference does).  idx [B,npoint] int64.                */
@@ -130,6 +139,19 @@ int b200pc_group_points(const float *xyz, const float *new_xyz, const float *fea
  * grad_feat[b, idx[b,s,k], d] += grad_out[b, (xyz_first ? 3 : 0) + d, k, s]                  */
 int b200pc_group_points_bwd(const float *grad_out, const int64_t *idx, int B, int N, int S, int K, int D,
                             int xyz_first, float *grad_feat, b200pc_stream_t stream);
+
+/* ---- a8 / f2: points-fusion grouping  Utils/Layers.py:207-226 (PointsFusion.knn_group), :384-402 (knn_group_withI), ----
+ *      PointINet20230424/models/layers.py:346-368; neighbour part of TransformerLayer.forward Utils/Layers.py:430-434     */
+/* qry [B,S,3] (points1), ref [B,N,3] (points2), feat [B,N,Cf] or NULL (Cf == 0).  One call = knn_points(qry, ref, K=k,
+ * return_nn=True) + resi + norm + cat + the three permute/contiguous copies:
+ *   resi  [B,4,S,k]  = (nn - q) in channels 0..2, |nn - q| in channel 3
+ *   nn    [B,3,S,k]  = the neighbours' coordinates
+ *   gfeat [B,Cf,S,k] = knn_gather(feat, idx) in Conv2d layout (NULL when Cf == 0)
+ *   idx   [B,S,k] int64, ascending (distance, index) like b200pc_knn(form 2); k <= N.
+ * workspace: b200pc_search_workspace_bytes(B, N, S, k).                                           */
+int b200pc_fusion_group(const float *qry, const float *ref, const float *feat, int B, int N, int S, int k, int Cf,
+                        float *resi, float *nn, float *gfeat, int64_t *idx, void *workspace, size_t workspace_bytes,
+                        b200pc_stream_t stream);
 
 /* ---- f4: PolyPCI polynomial fit + evaluation  ---------------------------
  *      PolyPCI/Models/Models_V1.py:116-124 (fitting_and_predict), call site :191-219           */

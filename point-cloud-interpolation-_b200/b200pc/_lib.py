@@ -31,6 +31,9 @@ SIGNATURES = {
     "b200pc_three_nn": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "b200pc_three_interpolate": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "b200pc_three_interpolate_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "b200pc_feature_propagation_workspace_bytes": (_z, [_i, _i, _i]),
+    "b200pc_feature_propagation": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "b200pc_fusion_group": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "b200pc_fps": (_i, [_p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "b200pc_fps_sample": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "b200pc_gather": (_i, [_p, _p, _i, _i, _i, _l, _p, _p, _p]),

@@ -10,11 +10,16 @@ therefore works on sys.modules:
      (only if the real pytorch3d is not importable, unless force=True);
   2. imports the reference's primitive module(s) and rebinds the four primitives in them and in
      every already-imported module that had bound the originals by name;
-  3. optionally (patch_layers=True) swaps the two layer methods whose hot path is INLINE code in
-     the reference -- `Group.forward` (kNN = square_distance + topk, Utils/Layers.py:50-53) and
-     `FeaturePropagation.forward` (three-NN = square_distance + full sort, Utils/Layers.py:180-188)
-     and `PointNetFeaturePropagation.forward` (Utils/Pointnet2Utils.py:297-304) -- for versions that
-     call knn_point / three_nn / three_interpolate, so no [B,N,M] matrix is ever materialised.
+  3. optionally (patch_layers=True) swaps the layer methods whose hot path is INLINE code in
+     the reference -- `Group.forward` (kNN = square_distance + topk, Utils/Layers.py:50-53),
+     `FeaturePropagation.forward` (three-NN = square_distance + full sort, Utils/Layers.py:180-188),
+     `PointNetFeaturePropagation.forward` (Utils/Pointnet2Utils.py:297-304),
+     `PointNetSetAbstractionMsg.forward` (grouping :240-253), `PointsFusion(.2).knn_group`
+     (Utils/Layers.py:207-226, upstream layers.py:346-368) and `knn_group_withI` (:384-402) -- for versions
+     that call knn_point / feature_propagation / group_points / fusion_group, so no [B,N,M] matrix is ever
+     materialised and each grouping is one C call.  Every replacement keeps the reference's tensor contract
+     and falls back to the reference's own differentiable torch composition (over the shim) when a coordinate
+     tensor requires grad.
 
 Call it once, before or after importing the reference's modules.
 """
@@ -29,34 +34,98 @@ from . import pointnet2_utils as P
 from . import pytorch3d_shim as shim
 
 _PRIMS = ("square_distance", "index_points", "farthest_point_sample", "query_ball_point")
+_MISSING = object()
+_UNDO = []          # (object, attribute, previous value or _MISSING), in the order install() changed them
+
+
+def _set(obj, name, value):
+    _UNDO.append((obj, name, obj.__dict__.get(name, _MISSING) if hasattr(obj, "__dict__") else getattr(obj, name, _MISSING)))
+    setattr(obj, name, value)
+
+
+def uninstall():
+    """undo every rebinding install() made (reference modules, classes, pytorch3d stand-ins), newest first"""
+    while _UNDO:
+        obj, name, old = _UNDO.pop()
+        if old is _MISSING:
+            try:
+                delattr(obj, name)
+            except AttributeError:
+                pass
+        else:
+            setattr(obj, name, old)
+    for name in [n for n, m in sys.modules.items() if getattr(m, "__b200pc_dropin_stub__", False)]:
+        del sys.modules[name]
 
 
 def _ensure_stub(name, **attrs):
     m = sys.modules.get(name)
     if m is None:
         m = types.ModuleType(name)
+        m.__b200pc_dropin_stub__ = True
         sys.modules[name] = m
     for k, v in attrs.items():
-        setattr(m, k, v)
+        _set(m, k, v)
     return m
 
 
+_P3D_NAMES = ("knn_points", "knn_gather", "chamfer_distance")
+
+
+def _imports_pytorch3d(mod):
+    """does this module's source bind names from pytorch3d (`from pytorch3d.ops import knn_points, knn_gather`)?"""
+    path = getattr(mod, "__file__", None)
+    if not path or not path.endswith(".py"):
+        return False
+    try:
+        with open(path, "r", errors="replace") as fh:
+            return "from pytorch3d" in fh.read()
+    except OSError:
+        return False
+
+
+def _is_stub(m):
+    return getattr(m, "__b200pc_dropin_stub__", False) or getattr(m, "__b200pc_stub__", False)
+
+
+def _real_pytorch3d():
+    m = sys.modules.get("pytorch3d.ops")
+    if m is not None:
+        return not _is_stub(m)
+    try:
+        importlib.import_module("pytorch3d.ops")
+        return True
+    except Exception:
+        return False
+
+
 def install_pytorch3d(force=False):
-    if not force:
-        try:
-            importlib.import_module("pytorch3d.ops")
-            return False
-        except Exception:
-            pass
+    """`pytorch3d.ops.knn_points / knn_gather` and `pytorch3d.loss.chamfer_distance` backed by the shim, unless a real
+    pytorch3d is importable (force=True replaces that too).  Modules that already bound the old functions by name
+    (`from pytorch3d.ops import knn_points`) are rebound as well."""
+    if _real_pytorch3d() and not force:
+        return False
     pkg = _ensure_stub("pytorch3d")
     if not hasattr(pkg, "__path__"):
-        pkg.__path__ = []          # mark as a package so `import pytorch3d.ops` resolves through sys.modules
-    pkg.ops = _ensure_stub("pytorch3d.ops", knn_points=shim.knn_points, knn_gather=shim.knn_gather)
-    pkg.loss = _ensure_stub("pytorch3d.loss", chamfer_distance=shim.chamfer_distance)
+        _set(pkg, "__path__", [])      # mark as a package so `import pytorch3d.ops` resolves through sys.modules
+    _set(pkg, "ops", _ensure_stub("pytorch3d.ops", knn_points=shim.knn_points, knn_gather=shim.knn_gather))
+    _set(pkg, "loss", _ensure_stub("pytorch3d.loss", chamfer_distance=shim.chamfer_distance))
+    for other in list(sys.modules.values()):
+        if other is None or not hasattr(other, "__dict__") or getattr(other, "__name__", "").startswith(("pytorch3d", "b200pc")):
+            continue
+        if not any(n in other.__dict__ for n in _P3D_NAMES) or not _imports_pytorch3d(other):
+            continue
+        for n in _P3D_NAMES:
+            if n in other.__dict__ and other.__dict__[n] is not getattr(shim, n):
+                _set(other, n, getattr(shim, n))
     return True
 
 
 # ---- replacement layer methods (same tensor contracts as the reference's) ---------------------
+def _wants_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 def _group_forward(self, points, new_points, features):
     """Group.forward, Utils/Layers.py:42-66: [B,3,N],[B,3,S],[B,D,N] -> [B,3+D,nsample,S]."""
     pts = points.permute(0, 2, 1).contiguous()
@@ -75,14 +144,22 @@ def _group_forward(self, points, new_points, features):
 
 
 def _fp_forward(self, points1, points2, features1, features2):
-    """FeaturePropagation.forward, Utils/Layers.py:174-192: [B,3,S],[B,3,N],[B,D1,S],[B,D2,N]."""
+    """FeaturePropagation.forward, Utils/Layers.py:174-192: [B,3,S],[B,3,N],[B,D1,S],[B,D2,N].  The weights carry
+    gradient to the coordinates when those require grad (ops.three_nn_autograd), like the reference's 1.0 / dists."""
     sparse = points1.permute(0, 2, 1).contiguous()
     dense = points2.permute(0, 2, 1).contiguous()
     feat = features1.permute(0, 2, 1).contiguous()
-    _, ind, w = P.three_nn_weights(dense, sparse, variant=0)
-    new = P.three_interpolate(feat, ind, w).permute(0, 2, 1).contiguous()
+    new = P.feature_propagation(dense, sparse, feat, variant=0).permute(0, 2, 1).contiguous()
     new = torch.cat([new, features2], dim=1)
     return self.conv(new.unsqueeze(3)).squeeze(3)
+
+
+def _norms(self, *names):
+    for n in names:
+        v = getattr(self, n, None)
+        if v is not None:
+            return v
+    raise AttributeError("none of %s on %s" % (names, type(self).__name__))
 
 
 def _pnfp_forward(self, xyz1, xyz2, points1, points2):
@@ -95,17 +172,68 @@ def _pnfp_forward(self, xyz1, xyz2, points1, points2):
     if S == 1:
         interp = feat.repeat(1, N, 1)
     else:
-        _, ind, w = P.three_nn_weights(dense, sparse, variant=1)
-        interp = P.three_interpolate(feat, ind, w)
+        interp = P.feature_propagation(dense, sparse, feat, variant=1)
     if points1 is not None:
         new = torch.cat([points1.permute(0, 2, 1), interp], dim=-1)
     else:
         new = interp
     new = new.permute(0, 2, 1)
-    norms = getattr(self, "mlp_gns", None) or getattr(self, "mlp_bns", None)
+    norms = _norms(self, "mlp_gns", "mlp_bns")
     for i, conv in enumerate(self.mlp_convs):
         new = F.relu(norms[i](conv(new)))
     return new
+
+
+def _samsg_forward(self, xyz, points):
+    """PointNetSetAbstractionMsg.forward, Utils/Pointnet2Utils.py:226-264: FPS + gather in one call, then per radius a
+    ball query and the fused grouping kernel in its features-first layout (xyz_first=False) -- the reference's
+    index_points x2, in-place centring, cat and permute (:243-253) never materialise."""
+    pts_xyz = xyz.permute(0, 2, 1)
+    feat = points.permute(0, 2, 1) if points is not None else None
+    B, N, _ = pts_xyz.shape
+    S = self.npoint
+    _, new_xyz = P.sample_points(pts_xyz, S)                       # draws torch.randint like farthest_point_sample (:76)
+    norms = _norms(self, "gn_blocks", "bn_blocks")
+    outs = []
+    for i, radius in enumerate(self.radius_list):
+        K = self.nsample_list[i]
+        group_idx = P.query_ball_point(radius, K, pts_xyz, new_xyz)
+        grouped = P.group_points(pts_xyz, new_xyz, feat, group_idx, xyz_first=False)     # [B, D+3, K, S]
+        for j, conv in enumerate(self.conv_blocks[i]):
+            grouped = F.relu(norms[i][j](conv(grouped)))
+        outs.append(torch.max(grouped, 2)[0])
+    return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+def _make_fusion_knn_group(original, with_features):
+    """PointsFusion.knn_group: fork signature (points1, points2, k) -> 2 tensors (Utils/Layers.py:207-226); upstream
+    signature (points1, points2, features2, k) -> 3 tensors (PointINet20230424/models/layers.py:346-368)."""
+    if with_features:
+        def knn_group(self, points1, points2, features2, k):
+            if k < 1 or _wants_grad(points1, points2, features2):
+                return original(self, points1, points2, features2, k)      # torch composition over the shim: differentiable
+            resi, nn, gf, _ = P.fusion_group(points1.permute(0, 2, 1), points2.permute(0, 2, 1), k, features2.permute(0, 2, 1))
+            return resi, nn, gf
+    else:
+        def knn_group(self, points1, points2, k):
+            if k < 1 or _wants_grad(points1, points2):
+                return original(self, points1, points2, k)
+            resi, nn, _, _ = P.fusion_group(points1.permute(0, 2, 1), points2.permute(0, 2, 1), k)
+            return resi, nn
+    knn_group.__doc__ = original.__doc__
+    knn_group._b200pc_original = original
+    return knn_group
+
+
+def _make_knn_group_withI(original):
+    def knn_group_withI(points1, points2, intensity2, k):
+        """knn_group_withI, Utils/Layers.py:384-402."""
+        if k < 1 or _wants_grad(points1, points2, intensity2):
+            return original(points1, points2, intensity2, k)
+        resi, nn, gf, _ = P.fusion_group(points1.permute(0, 2, 1), points2.permute(0, 2, 1), k, intensity2.permute(0, 2, 1))
+        return resi, nn, gf
+    knn_group_withI._b200pc_original = original
+    return knn_group_withI
 
 
 def _patch_module(mod, originals):
@@ -113,7 +241,7 @@ def _patch_module(mod, originals):
     for name in _PRIMS:
         cur = getattr(mod, name, None)
         if cur is not None and (cur is originals.get(name) or getattr(cur, "__module__", "") == mod.__name__):
-            setattr(mod, name, getattr(P, name))
+            _set(mod, name, getattr(P, name))
 
 
 def install(reference_modules=("Utils.Pointnet2Utils", "models.pointnet2_utils"), patch_layers=True,
@@ -135,15 +263,17 @@ def install(reference_modules=("Utils.Pointnet2Utils", "models.pointnet2_utils")
         originals = {n: getattr(mod, n, None) for n in _PRIMS}
         originals = {n: f for n, f in originals.items() if f is not None and f is not getattr(P, n)}
         for name in originals:
-            setattr(mod, name, getattr(P, name))
+            _set(mod, name, getattr(P, name))
         for other in list(sys.modules.values()):
             if other is None or other is mod or not hasattr(other, "__dict__"):
                 continue
             for name, fn in originals.items():
                 if other.__dict__.get(name) is fn:
-                    setattr(other, name, getattr(P, name))
+                    _set(other, name, getattr(P, name))
         if patch_layers and hasattr(mod, "PointNetFeaturePropagation"):
-            mod.PointNetFeaturePropagation.forward = _pnfp_forward
+            _set(mod.PointNetFeaturePropagation, "forward", _pnfp_forward)
+        if patch_layers and hasattr(mod, "PointNetSetAbstractionMsg"):
+            _set(mod.PointNetSetAbstractionMsg, "forward", _samsg_forward)
         patched.append(modname)
     if patch_layers:
         for lname in ("Utils.Layers", "models.layers"):
@@ -154,8 +284,19 @@ def install(reference_modules=("Utils.Pointnet2Utils", "models.pointnet2_utils")
                 except Exception:
                     continue
             if hasattr(lay, "Group"):
-                lay.Group.forward = _group_forward
+                _set(lay.Group, "forward", _group_forward)
             if hasattr(lay, "FeaturePropagation"):
-                lay.FeaturePropagation.forward = _fp_forward
+                _set(lay.FeaturePropagation, "forward", _fp_forward)
+            for cname in ("PointsFusion", "PointsFusion2"):
+                cls = getattr(lay, cname, None)
+                if cls is not None and not hasattr(cls.knn_group, "_b200pc_original"):
+                    nargs = cls.knn_group.__code__.co_argcount           # self, points1, points2, [features2,] k
+                    _set(cls, "knn_group", _make_fusion_knn_group(cls.knn_group, with_features=nargs == 5))
+            fn = getattr(lay, "knn_group_withI", None)
+            if fn is not None and not hasattr(fn, "_b200pc_original"):
+                new_fn = _make_knn_group_withI(fn)
+                for other in list(sys.modules.values()):                   # modules that imported it by name
+                    if other is not None and hasattr(other, "__dict__") and other.__dict__.get("knn_group_withI") is fn:
+                        _set(other, "knn_group_withI", new_fn)
             patched.append(lname)
     return patched

@@ -74,8 +74,28 @@ def three_nn(unknown, known):
 
 def three_nn_weights(unknown, known, variant=0):
     """three_nn plus the inverse-distance weights.  variant 0 = FeaturePropagation
-    (Utils/Layers.py:183-186), variant 1 = PointNetFeaturePropagation (Utils/Pointnet2Utils.py:301-303)."""
+    (Utils/Layers.py:183-186), variant 1 = PointNetFeaturePropagation (Utils/Pointnet2Utils.py:301-303).
+    When a coordinate tensor requires grad the distances and weights carry gradient to it, as the reference's
+    `1.0 / dists` does (ISAPCInet trains through them, Models/New_Models0.py:164-172)."""
+    if torch.is_grad_enabled() and (unknown.requires_grad or known.requires_grad):
+        return ops.three_nn_autograd(unknown, known, variant=variant)
     return ops.three_nn(unknown, known, variant=variant, want_weight=True)
+
+
+def feature_propagation(unknown, known, feats, variant=0):
+    """The interpolation of FeaturePropagation.forward (Utils/Layers.py:180-188, variant 0) /
+    PointNetFeaturePropagation.forward (Utils/Pointnet2Utils.py:297-304, variant 1) in one call:
+    unknown [B,N,3], known [B,S,3], feats [B,S,C] -> [B,N,C]; differentiable in feats, and in the coordinates
+    when they require grad."""
+    return ops.feature_propagation(unknown, known, feats, variant)
+
+
+def fusion_group(points1, points2, k, features2=None):
+    """PointsFusion.knn_group (Utils/Layers.py:207-226, PointINet20230424/models/layers.py:346-368) and
+    knn_group_withI (Utils/Layers.py:384-402) on point-major inputs: points1 [B,S,3] queries, points2 [B,N,3]
+    refs, features2 [B,N,Cf] or None -> (new_features [B,4,S,k], nn [B,3,S,k], grouped features [B,Cf,S,k],
+    idx [B,S,k]) from one C call (direct-form search + one feature kernel)."""
+    return ops.fusion_group(points1, points2, k, features2)
 
 
 def three_interpolate(feats, idx, weight):

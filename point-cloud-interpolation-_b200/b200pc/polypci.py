@@ -11,12 +11,10 @@ is linear in the data, so all N fits of a batch item share ONE weight vector
 float64; `fit_and_predict` applies it with one kernel (`b200pc_poly_predict`: float64 accumulation, one rounding to
 fp32) -- the point data never leaves the device.
 """
-import ctypes as C
-
 import numpy as np
 import torch
 
-from . import _lib
+from . import ops
 
 
 def poly_weights(T, t, degree):
@@ -53,9 +51,4 @@ def fit_and_predict(frames, T_list, t, degree):
     if w.shape[1] != F:
         raise ValueError("fit_and_predict: %d time stamps for %d frames" % (w.shape[1], F))
     wd = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
-    out = torch.empty_like(fr[0])
-    ptrs = (C.c_void_p * F)(*[C.c_void_p(f.data_ptr()) for f in fr])
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().b200pc_poly_predict(ptrs, C.c_void_p(wd.data_ptr()), B, F, per_batch, C.c_void_p(out.data_ptr()),
-                                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-    return out
+    return ops.poly_predict(fr, wd)

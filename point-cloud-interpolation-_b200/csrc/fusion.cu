@@ -1,0 +1,69 @@
+// fusion.cu -- points-fusion grouping in one C call.
+//
+// Replaces the body of PointsFusion.knn_group (Utils/Layers.py:207-226; upstream PointINet20230424/models/layers.py:346-368),
+// knn_group_withI (Utils/Layers.py:384-402) and the neighbour part of TransformerLayer.forward (Utils/Layers.py:430-434):
+//     _, nn_idx, nn = knn_points(points1, points2, K=k, return_nn=True)
+//     points_resi  = nn - points1.unsqueeze(2).repeat(1, 1, k, 1)
+//     grouped_dist = torch.norm(points_resi, dim=-1, keepdim=True)
+//     new_features = torch.cat([points_resi, grouped_dist], dim=-1).permute(0, 3, 1, 2).contiguous()     [B,4,S,k]
+//     nn.permute(0, 3, 1, 2).contiguous()                                                               [B,3,S,k]
+//     knn_gather(features2, nn_idx).permute(0, 3, 1, 2).contiguous()                                    [B,Cf,S,k]
+// which the reference runs as a search, two gathers and seven element-wise / copy kernels.  Here: the direct-form
+// top-k search (search.cu, form 2) followed by ONE kernel that reads each neighbour once and writes the three
+// Conv2d-layout tensors; thread e = (s, j) with j fastest, so every store instruction of a warp is 128 contiguous bytes
+// of one channel plane.  |resi| is sqrt((rx*rx + ry*ry) + rz*rz), every step rounded on its own like torch's
+// pow/sum/sqrt composition; values within 1e-5 relative of torch.norm (its accumulation order is not part of its contract).
+#include "common.cuh"
+#include "search.cuh"
+
+namespace b200pc {
+
+__global__ void __launch_bounds__(256) fusion_features_kernel(const float *__restrict__ qry, const float *__restrict__ ref,
+                                                              const float *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                              int N, int S, int K, int Cf, long total, float *__restrict__ resi,
+                                                              float *__restrict__ nn, float *__restrict__ gfeat) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;      // e = (b*S + s)*K + j : the layout of idx and of every output plane
+    if (e >= total) return;
+    const long bs = e / K;
+    const long b = bs / S;
+    const long plane = (long)S * K, o = e - b * plane;               // offset inside one [S,K] plane
+    const long i = idx[e];
+    const bool ok = i >= 0 && i < N;                                 // -1: a NaN query ranks nothing -> NaN features, like gathering nothing
+    const float *q = qry + bs * 3;
+    const float *r = ref + (b * N + (ok ? i : 0)) * 3;
+    const float qn = __int_as_float(0x7fc00000);
+    const float rx = ok ? __ldg(r + 0) : qn, ry = ok ? __ldg(r + 1) : qn, rz = ok ? __ldg(r + 2) : qn;
+    const float dx = __fsub_rn(rx, __ldg(q + 0)), dy = __fsub_rn(ry, __ldg(q + 1)), dz = __fsub_rn(rz, __ldg(q + 2));
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    float *ro = resi + b * 4 * plane + o;
+    __stcs(ro, dx); __stcs(ro + plane, dy); __stcs(ro + 2 * plane, dz); __stcs(ro + 3 * plane, __fsqrt_rn(n2));
+    float *no = nn + b * 3 * plane + o;
+    __stcs(no, rx); __stcs(no + plane, ry); __stcs(no + 2 * plane, rz);
+    if (Cf > 0) {
+        const float *fr = feat + (b * N + (ok ? i : 0)) * Cf;
+        float *go = gfeat + b * Cf * plane + o;
+        for (int c = 0; c < Cf; ++c) __stcs(go + c * plane, ok ? __ldg(fr + c) : qn);
+    }
+}
+
+}  // namespace b200pc
+
+using namespace b200pc;
+
+extern "C" int b200pc_fusion_group(const float *qry, const float *ref, const float *feat, int B, int N, int S, int k, int Cf,
+                                   float *resi, float *nn, float *gfeat, int64_t *idx, void *workspace, size_t workspace_bytes,
+                                   b200pc_stream_t stream) {
+    B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && k >= 1 && Cf >= 0, "fusion_group: bad sizes B=%d N=%d S=%d k=%d Cf=%d", B, N, S, k, Cf);
+    if (B == 0 || S == 0) return B200PC_OK;
+    B200PC_REQUIRE(qry && ref && resi && nn && idx, "fusion_group: null pointer");
+    B200PC_REQUIRE(Cf == 0 || (feat && gfeat), "fusion_group: Cf=%d feature channels but no feature pointers", Cf);
+    cudaStream_t st = as_stream(stream);
+    const int rc = run_topk(ref, qry, B, N, S, k, B200PC_FORM_DIRECT, idx, nullptr, workspace, workspace_bytes, st);
+    if (rc != B200PC_OK) return rc;
+    const long total = (long)B * S * k;
+    B200PC_REQUIRE((total + 255) / 256 < (1L << 31), "fusion_group: problem too large for one launch");
+    fusion_features_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qry, ref, Cf ? feat : nullptr, idx, N, S, k, Cf, total, resi,
+                                                                           nn, Cf ? gfeat : nullptr);
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}

@@ -401,3 +401,30 @@ extern "C" int b200pc_three_interpolate_bwd(const float *gout, const float *feat
     B200PC_LAUNCH_CHECK();
     return B200PC_OK;
 }
+
+
+// a5 in one call: FeaturePropagation.forward's interpolation (Utils/Layers.py:180-188) / PointNetFeaturePropagation's
+// (Utils/Pointnet2Utils.py:297-304): three-NN search -> inverse-distance weights -> weighted mix of the three rows.
+// The distances never leave the workspace; idx and weight are returned because the backward pass needs them.
+extern "C" size_t b200pc_feature_propagation_workspace_bytes(int B, int N, int S) {
+    if (B <= 0 || N <= 0 || S <= 0) return 256;
+    return align_up(b200pc_search_workspace_bytes(B, S, N, 3), 256) + align_up((size_t)B * N * 3 * sizeof(float), 256);
+}
+
+extern "C" int b200pc_feature_propagation(const float *unknown, const float *known, const float *feat, int B, int N, int S,
+                                          int C, int variant, float *out, int64_t *idx, float *weight, void *workspace,
+                                          size_t workspace_bytes, b200pc_stream_t stream) {
+    B200PC_REQUIRE(B >= 0 && N >= 0 && S >= 3 && C >= 1, "feature_propagation: bad sizes B=%d N=%d S=%d C=%d (needs S >= 3)", B, N, S, C);
+    if (B == 0 || N == 0) return B200PC_OK;
+    B200PC_REQUIRE(unknown && known && feat && out && idx && weight, "feature_propagation: null pointer");
+    const size_t search_bytes = align_up(b200pc_search_workspace_bytes(B, S, N, 3), 256);
+    if (!workspace || workspace_bytes < b200pc_feature_propagation_workspace_bytes(B, N, S)) {
+        set_error("feature_propagation: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                  b200pc_feature_propagation_workspace_bytes(B, N, S));
+        return B200PC_EWORKSPACE;
+    }
+    float *dist = reinterpret_cast<float *>(static_cast<char *>(workspace) + search_bytes);
+    int rc = b200pc_three_nn(unknown, known, B, N, S, variant, dist, idx, weight, workspace, search_bytes, stream);
+    if (rc != B200PC_OK) return rc;
+    return b200pc_three_interpolate(feat, idx, weight, B, S, N, C, out, stream);
+}

@@ -75,6 +75,43 @@ def test_fps_kernels_never_fuse_multiply_add():
         assert " FMUL " in text and " FADD " in text
 
 
+def test_torch_ops_mirror_the_header():
+    """every compute entry of include/b200pc.h is a registered torch.ops.b200pc.<name> (CUDA key only, with a fake
+    kernel), and no op exists without a C entry behind it"""
+    import torch
+    from b200pc import ops
+    not_ops = {"last_error", "version", "device_sm_count", "fma_peak"}
+    compute = {n[len("b200pc_"):] for n in declared_symbols()}
+    compute = {n for n in compute if n not in not_ops and not n.endswith("_workspace_bytes") and not n.endswith("_host")}
+    assert compute == set(ops.OP_SCHEMAS), compute ^ set(ops.OP_SCHEMAS)
+    for name in compute:
+        op = getattr(torch.ops.b200pc, name).default
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), "CUDA"), name
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), "CPU"), "%s must not have a CPU kernel" % name
+    with pytest.raises(NotImplementedError):        # the dispatcher itself refuses CPU tensors: no fallback
+        torch.ops.b200pc.knn(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3), 2, 0, False)
+    for name in ("gather", "group_points", "three_interpolate", "feature_propagation", "chamfer_fwd"):
+        op = getattr(torch.ops.b200pc, name).default
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), "Autograd"), name
+
+
+def test_fake_kernels_infer_shapes_without_a_gpu():
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from b200pc import ops  # noqa: F401
+    with FakeTensorMode():
+        ref = torch.empty(2, 100, 3, device="cuda"); qry = torch.empty(2, 50, 3, device="cuda")
+        idx, dist = torch.ops.b200pc.knn(ref, qry, 4, 0, True)
+        assert idx.shape == (2, 50, 4) and idx.dtype == torch.int64 and dist.shape == (2, 50, 4)
+        assert torch.ops.b200pc.ball_query(ref, qry, 1.0, 8).shape == (2, 50, 8)
+        feat = torch.empty(2, 100, 16, device="cuda")
+        assert torch.ops.b200pc.group_points(ref, qry, feat, idx, True).shape == (2, 19, 4, 50)
+        resi, nn, gf, i2 = torch.ops.b200pc.fusion_group(qry, ref, feat, 8)
+        assert resi.shape == (2, 4, 50, 8) and nn.shape == (2, 3, 50, 8) and gf.shape == (2, 16, 50, 8) and i2.shape == (2, 50, 8)
+        out, i3, w3 = torch.ops.b200pc.feature_propagation(ref, qry, torch.empty(2, 50, 32, device="cuda"), 0)
+        assert out.shape == (2, 100, 32) and i3.shape == (2, 100, 3) and w3.shape == (2, 100, 3)
+
+
 def test_version_and_workspace_queries_need_no_gpu():
     lib = _lib.load()
     assert lib.b200pc_version() >= 100
