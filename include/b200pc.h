@@ -47,6 +47,9 @@ const char *b200pc_last_error(void);
 int b200pc_version(void);
 /* number of SMs of the current device, or a negative error code */
 int b200pc_device_sm_count(void);
+/* The B200PC_* tuning / debugging environment variables are read once, at the first launch, and cached (a launch never
+ * calls getenv); this re-reads them.  For tests and A/B probes only -- the variables are not part of the ABI. */
+void b200pc_tuning_reload(void);
 
 /* ---- scratch sizing -------------------------------------------------------------------- */
 /* scratch for any neighbour search (knn / ball_query / three_nn / chamfer) of S queries

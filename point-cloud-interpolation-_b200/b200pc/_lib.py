@@ -23,6 +23,7 @@ SIGNATURES = {
     "b200pc_last_error": (C.c_char_p, []),
     "b200pc_version": (_i, []),
     "b200pc_device_sm_count": (_i, []),
+    "b200pc_tuning_reload": (None, []),
     "b200pc_search_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "b200pc_fps_workspace_bytes": (_z, [_i, _i]),
     "b200pc_square_distance": (_i, [_p, _p, _i, _i, _i, _p, _p]),

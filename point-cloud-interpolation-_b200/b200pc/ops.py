@@ -26,6 +26,10 @@ CHECK_BOUNDS = os.environ.get("B200PC_CHECK_BOUNDS", "0") == "1"
 
 launch_count = 0     # C-ABI compute calls issued (bench.py reports kernels from the plan below)
 
+# The library reads its B200PC_* tuning variables once and caches them.  Probes that flip a knob between calls set this
+# to True (or call reload_tuning() themselves): the cache is then refreshed before every C call.
+TUNING_AUTORELOAD = False
+
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
@@ -60,6 +64,8 @@ def _workspace(nbytes, dev):
 def _call(dev, fn, *args):
     """one C-ABI compute call on `dev` (current stream), error code -> exception"""
     global launch_count
+    if TUNING_AUTORELOAD:
+        _lib.load().b200pc_tuning_reload()
     with torch.cuda.device(dev):
         _lib.check(fn(*args))
     launch_count += 1
@@ -581,6 +587,11 @@ def chamfer(x, y):
 def poly_predict(frames, weights):
     """frames: list of F [B,...] fp32 CUDA tensors, weights [B,F] float64 on the device -> sum_f w[b,f] * frames[f][b]"""
     return _O.poly_predict([_prep(f, "frame") for f in frames], weights.contiguous())
+
+
+def reload_tuning():
+    """re-read the B200PC_* tuning variables (the library caches them at its first launch); tests / probes only"""
+    _lib.load().b200pc_tuning_reload()
 
 
 def fma_peak(iters=4096):

@@ -1,6 +1,7 @@
 // api.cu -- ABI plumbing of libb200pc.so: error reporting, device queries, the FP32 peak
 // micro-benchmark and the host-buffer convenience wrappers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -37,6 +38,39 @@ int sm_count() {
     return cached;
 }
 
+static int env_int(const char *name, int unset) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : unset;
+}
+
+static Tuning g_tuning;
+static bool g_tuning_loaded = false;
+
+static void load_tuning() {
+    Tuning t;
+    t.force_q = env_int("B200PC_FORCE_Q", 0);
+    t.force_warps = env_int("B200PC_FORCE_WARPS", 0);
+    t.force_split = env_int("B200PC_FORCE_SPLIT", 0);
+    t.natural_order = env_int("B200PC_NATURAL_ORDER", -1);
+    t.nodrain = getenv("B200PC_DEBUG_NODRAIN") != nullptr;
+    t.filter = env_int("B200PC_FILTER", -1);
+    t.small_path = env_int("B200PC_SMALL_PATH", -1);
+    t.gather_rows = env_int("B200PC_GATHER_ROWS", -1);
+    t.gather_flat = env_int("B200PC_GATHER_FLAT", -1);
+    t.interp_rows = env_int("B200PC_INTERP_ROWS", -1);
+    t.interp_flat = env_int("B200PC_INTERP_FLAT", -1);
+    t.bulk = env_int("B200PC_BULK", -1);
+    t.fps_cluster = env_int("B200PC_FPS_CLUSTER", 0);
+    t.drain = env_int("B200PC_DRAIN", -1);
+    g_tuning = t;
+    g_tuning_loaded = true;
+}
+
+const Tuning &tuning() {
+    if (!g_tuning_loaded) load_tuning();
+    return g_tuning;
+}
+
 // 8 independent packed-FMA chains per thread, fully register resident
 __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float *sink) {
     f32x2 a[8];
@@ -58,7 +92,8 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
 using namespace b200pc;
 
 extern "C" const char *b200pc_last_error(void) { return g_err; }
-extern "C" int b200pc_version(void) { return 100; }
+extern "C" int b200pc_version(void) { return 200; }
+extern "C" void b200pc_tuning_reload(void) { load_tuning(); }
 
 extern "C" int b200pc_device_sm_count(void) {
     int dev = -1, n = 0;
@@ -67,43 +102,46 @@ extern "C" int b200pc_device_sm_count(void) {
     return n;
 }
 
-extern "C" int b200pc_fma_peak(int iters, double *tflops, double *ms_out, b200pc_stream_t stream) {
-    B200PC_REQUIRE(iters > 0 && tflops, "fma_peak: bad arguments");
-    cudaStream_t st = as_stream(stream);
-    const int sms = sm_count();
-    const int blocks = sms * 8, threads = 256;
-    float *sink = nullptr;
-    B200PC_CUDA(cudaMalloc(&sink, sizeof(float)));
-    cudaEvent_t e0, e1;
-    B200PC_CUDA(cudaEventCreate(&e0));
-    B200PC_CUDA(cudaEventCreate(&e1));
-    fma_peak_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, 0.5f, sink);  // warm-up
-    B200PC_CUDA(cudaEventRecord(e0, st));
-    fma_peak_kernel<<<blocks, threads, 0, st>>>(iters, 0.5f, sink);
-    B200PC_CUDA(cudaEventRecord(e1, st));
-    B200PC_CUDA(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    B200PC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    const double flop = (double)blocks * threads * (double)iters * 8.0 /*chains*/ * 2.0 /*lanes*/ * 2.0 /*mul+add*/;
-    *tflops = flop / (ms * 1e-3) / 1e12;
-    if (ms_out) *ms_out = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(sink);
-    return B200PC_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// host-buffer wrappers: for callers without a device allocator of their own
-// ------------------------------------------------------------------------------------------------
 namespace {
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
 };
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
 }  // namespace
 
+extern "C" int b200pc_fma_peak(int iters, double *tflops, double *ms_out, b200pc_stream_t stream) {
+    B200PC_REQUIRE(iters > 0 && tflops, "fma_peak: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const int sms = sm_count();
+    const int blocks = sms * 8, threads = 256;
+    DevBuf sink;                        // RAII: nothing leaks on an early error return
+    EventPair ev;
+    B200PC_CUDA(sink.alloc(sizeof(float)));
+    B200PC_CUDA(cudaEventCreate(&ev.a));
+    B200PC_CUDA(cudaEventCreate(&ev.b));
+    fma_peak_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, 0.5f, static_cast<float *>(sink.p));  // warm-up
+    B200PC_LAUNCH_CHECK();
+    B200PC_CUDA(cudaEventRecord(ev.a, st));
+    fma_peak_kernel<<<blocks, threads, 0, st>>>(iters, 0.5f, static_cast<float *>(sink.p));
+    B200PC_LAUNCH_CHECK();
+    B200PC_CUDA(cudaEventRecord(ev.b, st));
+    B200PC_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0.f;
+    B200PC_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    const double flop = (double)blocks * threads * (double)iters * 8.0 /*chains*/ * 2.0 /*lanes*/ * 2.0 /*mul+add*/;
+    *tflops = flop / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return B200PC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer wrappers: for callers without a device allocator of their own
+// ------------------------------------------------------------------------------------------------
 extern "C" int b200pc_knn_host(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
                                float *dist) {
     B200PC_REQUIRE(ref && qry && idx, "knn_host: null pointer");

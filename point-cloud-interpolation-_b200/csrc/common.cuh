@@ -37,6 +37,22 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int sm_count();
 
+// Tuning / debugging knobs (B200PC_* environment variables; NOT part of the ABI).  They are read ONCE, at the first
+// launch, and cached -- a launch never calls getenv.  b200pc_tuning_reload() re-reads them (tests and A/B probes that
+// flip a knob between calls).  -1 = not set (the launcher's own default applies).
+struct Tuning {
+    int force_q, force_warps, force_split;   // search planner overrides (0 = none)
+    int natural_order;                       // top-k refs kept in index order (1) / dealt out strided (0)
+    int nodrain;                             // measurement only: the search starts with tau = -inf
+    int filter;                              // 0: broadcast filter on every tile (the v6 hot loop)
+    int small_path;                          // 0 / 1: forbid / force the warp-per-query path
+    int gather_rows, gather_flat, interp_rows, interp_flat;
+    int bulk;                                // 0: register-path row movers (gather.cu / group.cu) instead of rowmove.cu
+    int fps_cluster;
+    int drain;                               // search drain variant (A/B)
+};
+const Tuning &tuning();
+
 // ---------------------------------------------------------------------------------------------
 // packed fp32x2 arithmetic.  A "pair" is a 64-bit register holding two IEEE fp32 lanes; each op
 // rounds both lanes to nearest-even independently, exactly like the scalar instruction would.

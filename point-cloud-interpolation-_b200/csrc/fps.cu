@@ -209,8 +209,8 @@ static void fps_shape(int B, int N, int *C_out, int *P_out) {
     while (C < FPS_MAX_CLUSTER && (long)C * FPS_T * 16 < N) C *= 2;
     if (C > 1)
         while (C < 8 && (long)B * C * 4 <= sms && (long)C * FPS_T * 4 < N) C *= 2;
-    if (const char *e = getenv("B200PC_FPS_CLUSTER")) {   // tuning override (not part of the ABI)
-        const int f = atoi(e);
+    {   // tuning override (cached; not part of the ABI)
+        const int f = tuning().fps_cluster;
         if (f >= 1 && f <= FPS_MAX_CLUSTER && (long)f * FPS_T * 16 >= N) C = f;
     }
     int P = 1;

@@ -12,6 +12,10 @@
 
 namespace b200pc {
 
+// rowmove.cu: the TMA (cp.async.bulk) row movers; -100 = shape not served
+int gather_bulk(const float *points, const int64_t *idx, int B, int N, int C, long R, float *out, int *oob, cudaStream_t st);
+int interp_bulk(const float *feat, const int64_t *idx, const float *w, int B, int S, int N, int C, float *out, cudaStream_t st);
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int wave_grid(long work_items, int threads, int per_thread) {
@@ -305,10 +309,13 @@ extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
         const long rows = (long)B * R;
-        const char *tune = getenv("B200PC_GATHER_ROWS");   // tuning override (not part of the ABI)
-        const int rw = tune ? atoi(tune) : 8;
-        const char *flat = getenv("B200PC_GATHER_FLAT");        // default: flat for narrow rows (a warp per row idles lanes when C < 128)
-        if (flat ? atoi(flat) != 0 : C / 4 < 32) {
+        const Tuning &tn = tuning();                        // cached knobs (not part of the ABI)
+        if (tn.bulk != 0) {                                 // rows of >= 128 bytes: the TMA path (rowmove.cu)
+            const int rc = gather_bulk(points, idx, B, N, C, (long)R, out, oob_flag, st);
+            if (rc != -100) return rc;
+        }
+        const int rw = tn.gather_rows > 0 ? tn.gather_rows : 8;
+        if (tn.gather_flat >= 0 ? tn.gather_flat != 0 : C / 4 < 32) {   // default: flat for narrow rows (a warp per row idles lanes when C < 128)
             const long total = rows * (C / 4);
             gather_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(points), idx, N, C / 4,
                                                                                (long)R, total, reinterpret_cast<float4 *>(out), oob_flag);
@@ -371,12 +378,15 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
     cudaStream_t st = as_stream(stream);
     if (C % 4 == 0 && aligned16(feat) && aligned16(out) && (long)B * S * (C / 4) < (1L << 31)) {
         const long rows = (long)B * N;
-        const char *tune = getenv("B200PC_INTERP_ROWS");   // tuning override (not part of the ABI)
-        const int rw = tune ? atoi(tune) : 2;
+        const Tuning &tn = tuning();                        // cached knobs (not part of the ABI)
+        if (tn.bulk > 0) {                                  // opt-in: the TMA path measured no faster here (bound by L2 -> SM row traffic)
+            const int rc = interp_bulk(feat, idx, weight, B, S, N, C, out, st);
+            if (rc != -100) return rc;
+        }
+        const int rw = tn.interp_rows > 0 ? tn.interp_rows : 2;
         const float4 *f4 = reinterpret_cast<const float4 *>(feat);
         float4 *o4 = reinterpret_cast<float4 *>(out);
-        const char *flat = getenv("B200PC_INTERP_FLAT");        // default: flat for narrow rows (C < 128)
-        if (flat ? atoi(flat) != 0 : C / 4 < 32) {
+        if (tn.interp_flat >= 0 ? tn.interp_flat != 0 : C / 4 < 32) {   // default: flat for narrow rows (C < 128)
             const long total = rows * (C / 4);
             interp_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, total, o4);
         } else if (rw == 8) interp_rows_kernel<8><<<wave_grid(rows * 32 / 8, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);

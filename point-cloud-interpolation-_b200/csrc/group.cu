@@ -13,6 +13,9 @@
 
 namespace b200pc {
 
+int group_bulk(const float *xyz, const float *new_xyz, const float *feat, const int64_t *idx, int B, int N, int S, int K, int D,
+               int xyz_first, float *out, cudaStream_t st);   // rowmove.cu; -100 = shape not served
+
 constexpr int GROUP_S = 32;       // centres per block tile of the backward kernel
 
 __device__ __forceinline__ long wrap_index(long i, int N) { return i < 0 ? i + N : i; }   // torch advanced indexing
@@ -111,6 +114,10 @@ extern "C" int b200pc_group_points(const float *xyz, const float *new_xyz, const
     const long total = (long)B * K * S;
     B200PC_REQUIRE((total + 255) / 256 < (1L << 31), "group_points: problem too large for one launch");
     const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (tuning().bulk != 0 && D > 0) {                      // wide feature rows: the TMA path (rowmove.cu)
+        const int rc = group_bulk(xyz, new_xyz, feat, idx, B, N, S, K, D, xyz_first != 0, out, as_stream(stream));
+        if (rc != -100) return rc;
+    }
     if (D > 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0)
         group_points_direct4_kernel<<<blocks, 256, 0, as_stream(stream)>>>(xyz, new_xyz, reinterpret_cast<const float4 *>(feat), idx, N, S,
                                                                           K, D, xyz_first != 0, total, out);

@@ -684,10 +684,8 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     pl->n_pad = (int)align_up((size_t)N, TILE);
     pl->n_tiles = pl->n_pad / TILE;
 
-    int force_q = 0, force_w = 0, force_split = 0;   // tuning / debugging overrides (not part of the ABI)
-    if (const char *e = getenv("B200PC_FORCE_Q")) force_q = atoi(e);
-    if (const char *e = getenv("B200PC_FORCE_WARPS")) force_w = atoi(e);
-    if (const char *e = getenv("B200PC_FORCE_SPLIT")) force_split = atoi(e);
+    const Tuning &tn = tuning();                      // tuning / debugging overrides (cached; not part of the ABI)
+    const int force_q = tn.force_q, force_w = tn.force_warps, force_split = tn.force_split;
 
     double best_score = -1.0;
     int best_q = 1, best_w = 1, best_split = 1;
@@ -790,8 +788,8 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     // top-k: refs dealt out to the tiles in a strided order (see slot_to_ref).  Not for form 1: its only caller is three-NN
     // feature propagation, whose reference points are FPS picks -- an order that is already ideal for a running k-best
     // (every prefix is a well-spread sample; measured 0.32 ms natural vs 0.36 ms strided on C3).
-    const char *order_env = getenv("B200PC_NATURAL_ORDER");
-    const int strided = mode == MODE_TOPK && (order_env ? atoi(order_env) == 0 : form != B200PC_FORM_QRY_NORM_FIRST);
+    const Tuning &tn = tuning();
+    const int strided = mode == MODE_TOPK && (tn.natural_order >= 0 ? tn.natural_order == 0 : form != B200PC_FORM_QRY_NORM_FIRST);
     {
         dim3 grid((pl.n_pad / 2 + 255) / 256, B);
         pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, strided, packed);
@@ -800,9 +798,8 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     SearchArgs a;
     a.packed = packed; a.strided = strided; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
-    a.debug_nodrain = getenv("B200PC_DEBUG_NODRAIN") != nullptr;
-    a.lane_filter = 1;
-    if (const char *e = getenv("B200PC_FILTER")) a.lane_filter = atoi(e) != 0;   // A/B measurement only
+    a.debug_nodrain = tn.nodrain;
+    a.lane_filter = tn.filter >= 0 ? tn.filter != 0 : 1;                          // 0: A/B measurement only
     a.idx_out = idx; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;

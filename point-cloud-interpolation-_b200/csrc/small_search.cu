@@ -138,7 +138,8 @@ static int launch_small(const float *ref, const float *qry, int B, int N, int S,
 int run_small(const float *ref, const float *qry, int B, int N, int S, int k, int form, int mode, float r2, int64_t *idx,
               float *dist, cudaStream_t st) {
     if (N > SMALL_MAX_N) return -100;
-    if (const char *e = getenv("B200PC_SMALL_PATH")) { if (atoi(e) == 0) return -100; }
+    const int forced = tuning().small_path;             // cached knob (-1: decide by size)
+    if (forced >= 0) { if (forced == 0) return -100; }
     else {
         // per query: ~N/32*6 instructions of distances + k*(N/32*3+20) of selection per WARP, against
         // ~N*6/32 + k(1+ln(N/k))*100/32 per warp-lane in the streaming kernel: worth it for few queries or big k

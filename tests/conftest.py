@@ -29,3 +29,13 @@ def cuda_dev():
 def _oracle_built():
     from oracle import strict
     strict.build()
+
+
+@pytest.fixture(autouse=True)
+def _fresh_tuning():
+    """the library caches its B200PC_* tuning variables; re-read them once a test that changed the environment
+    (monkeypatch.setenv + ops.reload_tuning()) is over, so knobs never leak into the next test"""
+    yield
+    from b200pc import _lib
+    if _lib._lib is not None:
+        _lib._lib.b200pc_tuning_reload()

@@ -43,7 +43,7 @@ def test_knn_matches_strict_oracle(cuda_dev, monkeypatch, B, N, S, k, form, smal
     if small_path == "0":
         if N > 1024:
             pytest.skip("streaming kernel is the only path for N > 1024")
-        monkeypatch.setenv("B200PC_SMALL_PATH", "0")
+        monkeypatch.setenv("B200PC_SMALL_PATH", "0"); ops.reload_tuning()
     a, b = synth.batch_pairs(10, B, max(N, S))
     ref, qry = a[:, :N].copy(), b[:, :S].copy()
     idx, dist = ops.knn_search(_t(ref, cuda_dev), _t(qry, cuda_dev), k, form, want_dist=True)
@@ -117,7 +117,7 @@ def test_ball_query_matches_strict_oracle(cuda_dev, monkeypatch, B, N, S, radius
     if small_path == "0":
         if N > 1024:
             pytest.skip("streaming kernel is the only path for N > 1024")
-        monkeypatch.setenv("B200PC_SMALL_PATH", "0")
+        monkeypatch.setenv("B200PC_SMALL_PATH", "0"); ops.reload_tuning()
     a, b = synth.batch_pairs(20, B, max(N, S))
     xyz, new_xyz = a[:, :N].copy(), b[:, :S].copy()
     out = P.query_ball_point(radius, nsample, _t(xyz, cuda_dev), _t(new_xyz, cuda_dev))

@@ -2,6 +2,7 @@ import os, sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/point-cloud-interpolation-_b200")
 import torch
 from b200pc import ops, synth
+import b200pc.ops as _b200pc_ops; _b200pc_ops.TUNING_AUTORELOAD = True   # this probe flips B200PC_* knobs between calls (the library caches them)
 dev = torch.device("cuda:0")
 a, b = synth.batch_pairs(0, 1, 16384)
 ref = torch.from_numpy(a).to(dev); qry = torch.from_numpy(b).to(dev)

@@ -6,6 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "point-cloud-int
 import numpy as np
 import torch
 from b200pc import ops, pointnet2_utils as P
+import b200pc.ops as _b200pc_ops; _b200pc_ops.TUNING_AUTORELOAD = True   # this probe flips B200PC_* knobs between calls (the library caches them)
 from oracle import strict
 
 

@@ -4,6 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "point-cloud-interpolation-_b200"))
 import torch
 from b200pc import pointnet2_utils as P
+import b200pc.ops as _b200pc_ops; _b200pc_ops.TUNING_AUTORELOAD = True   # this probe flips B200PC_* knobs between calls (the library caches them)
 dev = torch.device("cuda:0")
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 def t(fn, n=10):

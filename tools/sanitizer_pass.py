@@ -4,6 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "point-cloud-interpolation-_b200"))
 import torch
 from b200pc import ops, pointnet2_utils as P, pytorch3d_shim as S3, synth
+import b200pc.ops as _b200pc_ops; _b200pc_ops.TUNING_AUTORELOAD = True   # this probe flips B200PC_* knobs between calls (the library caches them)
 dev = torch.device("cuda:0")
 a, b = synth.batch_pairs(0, 2, 3000)
 ref = torch.from_numpy(a).to(dev); qry = torch.from_numpy(b[:, :700].copy()).to(dev)
