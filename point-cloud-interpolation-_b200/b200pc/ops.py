@@ -66,8 +66,11 @@ def _call(dev, fn, *args):
     global launch_count
     if TUNING_AUTORELOAD:
         _lib.load().b200pc_tuning_reload()
-    with torch.cuda.device(dev):
+    if dev.index == torch.cuda.current_device():        # the common case: no device switch around the call
         _lib.check(fn(*args))
+    else:
+        with torch.cuda.device(dev):
+            _lib.check(fn(*args))
     launch_count += 1
 
 

@@ -310,7 +310,7 @@ extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
         const long rows = (long)B * R;
         const Tuning &tn = tuning();                        // cached knobs (not part of the ABI)
-        if (tn.bulk != 0) {                                 // rows of >= 128 bytes: the TMA path (rowmove.cu)
+        if (tn.bulk > 0) {                                  // opt-in (B200PC_BULK=1): the asynchronous-copy path (rowmove.cu), see its header
             const int rc = gather_bulk(points, idx, B, N, C, (long)R, out, oob_flag, st);
             if (rc != -100) return rc;
         }
@@ -379,7 +379,7 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
     if (C % 4 == 0 && aligned16(feat) && aligned16(out) && (long)B * S * (C / 4) < (1L << 31)) {
         const long rows = (long)B * N;
         const Tuning &tn = tuning();                        // cached knobs (not part of the ABI)
-        if (tn.bulk > 0) {                                  // opt-in: the TMA path measured no faster here (bound by L2 -> SM row traffic)
+        if (tn.bulk > 0) {                                  // opt-in (B200PC_BULK=1): the asynchronous-copy path (rowmove.cu), see its header
             const int rc = interp_bulk(feat, idx, weight, B, S, N, C, out, st);
             if (rc != -100) return rc;
         }

@@ -114,7 +114,7 @@ extern "C" int b200pc_group_points(const float *xyz, const float *new_xyz, const
     const long total = (long)B * K * S;
     B200PC_REQUIRE((total + 255) / 256 < (1L << 31), "group_points: problem too large for one launch");
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (tuning().bulk != 0 && D > 0) {                      // wide feature rows: the TMA path (rowmove.cu)
+    if (tuning().bulk > 0 && D > 0) {                       // opt-in (B200PC_BULK=1): the asynchronous-copy path (rowmove.cu)
         const int rc = group_bulk(xyz, new_xyz, feat, idx, B, N, S, K, D, xyz_first != 0, out, as_stream(stream));
         if (rc != -100) return rc;
     }

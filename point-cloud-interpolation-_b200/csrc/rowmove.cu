@@ -1,26 +1,30 @@
-// rowmove.cu -- the HBM-bound row movers on the TMA path (sm_100a): whole feature rows travel global -> shared with one
-// cp.async.bulk per row (SASS UBLKCP), completion is counted on per-warp mbarriers, and rows leave either as ONE bulk
-// store per group of consecutive output rows (index_points) or after a register pass (three_interpolate, group_points).
+// rowmove.cu -- the HBM-bound row movers on the asynchronous-copy path (sm_100a): feature rows travel global -> shared
+// with warp-cooperative 16-byte cp.async (SASS LDGSTS: no register is held while a row is in flight, a 512-byte row is
+// ONE instruction), stages complete through cp.async groups, and rows leave either as ONE bulk TMA store
+// (cp.async.bulk, SASS UBLKCP) per group of consecutive output rows (index_points) or after a register pass
+// (three_interpolate, group_points).
 //
-//   gather_bulk_kernel   index_points            Utils/Pointnet2Utils.py:44-61 (= pytorch3d knn_gather, Utils/Layers.py:396,434)
-//   interp_bulk_kernel   three_interpolate       Utils/Layers.py:187-188, Utils/Pointnet2Utils.py:304
-//   group_bulk_kernel    Group.forward tail      Utils/Layers.py:57-66, SA-MSG grouping Utils/Pointnet2Utils.py:243-253
+//   gather_async_kernel   index_points            Utils/Pointnet2Utils.py:44-61 (= pytorch3d knn_gather, Utils/Layers.py:396,434)
+//   interp_async_kernel   three_interpolate       Utils/Layers.py:187-188, Utils/Pointnet2Utils.py:304
+//   group_async_kernel    Group.forward tail      Utils/Layers.py:57-66, SA-MSG grouping Utils/Pointnet2Utils.py:243-253
 //
 // Why: the register-path kernels of gather.cu / group.cu buy memory-level parallelism with registers (8 rows in flight =
-// 73 registers, 28 % of the warp slots; 4 rows of three_interpolate = 121 registers) and pay one L1 wavefront per 32-byte
-// sector of every gathered row (group_points: 580 wavefront-cycles per 8 KB of output -- the measured 3.5 TB/s is exactly
-// that bound).  A bulk copy costs one instruction per ROW, holds no register while in flight, and writes shared memory
-// without passing the LSU, so a CTA keeps 100-190 KB in flight with 4 warps.  Every warp runs its own ring of stages
-// (no block barrier after set-up); work is dealt to the warps in groups small enough that the last wave is > 95 % full.
+// 73 registers, 28 % of the warp slots; 4 rows of three_interpolate = 121 registers), and group_points pays one L1
+// wavefront per 32-byte sector of every gathered row because each lane walks its OWN row (580 wavefront-cycles per 8 KB
+// of output: the measured 3.5 TB/s is exactly that bound).  Here a warp copies whole rows cooperatively (coalesced), a
+// CTA keeps 100-190 KB in flight, every warp runs its own ring of stages (no block barrier at all), and work is dealt
+// out in groups small enough that the last wave is > 85 % full.
+// Measured dead end, kept out: one cp.async.bulk PER ROW (TMA gather).  The TMA unit serves ~1 request per 46-60 cycles
+// per SM whatever its size, i.e. 10 B/clk/SM for 512-byte rows -- three_interpolate went from 60 us to 163 us,
+// group_points from 108 us to 167 us (profiles/r02_notes.md).  Bulk copies are used where one request moves >= 4 KB.
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace b200pc {
 
-constexpr int RM_WARPS = 4;                       // warps per CTA, one CTA per SM
-constexpr int RM_BAR_AREA = 256;                  // mbarriers: RM_WARPS x up to 8 stages x 8 bytes
-constexpr size_t RM_SMEM_BUDGET = 200 * 1024;     // per CTA, leaves room for the driver's reservation
+constexpr int RM_BAR_AREA = 0;
+constexpr size_t RM_SMEM_BUDGET = 200 * 1024;     // per CTA (one CTA per SM), leaves room for the driver's reservation
 
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
@@ -31,6 +35,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void sts_zero16(uint32_t a) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
 }
@@ -45,153 +55,151 @@ __device__ __forceinline__ float lds_f1(uint32_t a) {
     return v;
 }
 
-// per-warp ring set-up: NST mbarriers (one arrival each: the lane that posts the byte count)
-template <int NST>
-__device__ __forceinline__ uint32_t ring_init(unsigned char *smem, int warp, int lane) {
-    const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * NST) * 8u;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8u * s, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-    return bar0;
+// One row (row_bytes, a multiple of 16) global -> shared by the whole warp; src == nullptr: a row of zeros.
+__device__ __forceinline__ void warp_copy_row(uint32_t dst, const char *src, uint32_t row_bytes, int lane) {
+    if (src) { for (uint32_t o = 16u * lane; o < row_bytes; o += 512u) cp_async16(dst + o, src + o); }
+    else { for (uint32_t o = 16u * lane; o < row_bytes; o += 512u) sts_zero16(dst + o); }
 }
 
 // ---------------------------------------------------------------------------------------------
-// index_points: out[row, :] = points[b(row), idx[row], :]
-// A group = RS consecutive output rows = one contiguous block of the output: RS bulk loads in, ONE bulk store out.
+// All index arithmetic below is 32-bit (the launchers check rows, B*N and B*S against 2^31): a 64-bit division is a
+// ~100-instruction subroutine call, and these kernels run 4-8 warps per SM -- they are bound by the instruction stream
+// of a single warp per scheduler, not by a pipe (ncu of the first version: 258 instructions per interpolated row).
 // ---------------------------------------------------------------------------------------------
+// index_points: out[row, :] = points[b(row), idx[row], :]
+// A group = RS consecutive output rows = one contiguous block of the output: RS row copies in, ONE bulk store out.
+// ---------------------------------------------------------------------------------------------
+constexpr int GA_WARPS = 8;
+
 template <int NST>
-__global__ void __launch_bounds__(RM_WARPS * 32, 1) gather_bulk_kernel(const char *__restrict__ points, const int64_t *__restrict__ idx,
-                                                                       int N, uint32_t row_bytes, int RS, long R, long rows_total,
-                                                                       char *__restrict__ out, int *__restrict__ oob) {
+__global__ void __launch_bounds__(GA_WARPS * 32, 1) gather_async_kernel(const char *__restrict__ points, const int64_t *__restrict__ idx,
+                                                                        int N, uint32_t row_bytes, int RS, int R, int rows_total,
+                                                                        char *__restrict__ out, int *__restrict__ oob) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stage_bytes = (uint32_t)RS * row_bytes;
-    const uint32_t bar0 = ring_init<NST>(smem, warp, lane);
-    const uint32_t data0 = smem_u32(smem) + RM_BAR_AREA + (uint32_t)(warp * NST) * stage_bytes;
-    const long groups = (rows_total + RS - 1) / RS;
-    const long gw = (long)blockIdx.x * RM_WARPS + warp, nw = (long)gridDim.x * RM_WARPS;
-    const long n_my = groups > gw ? (groups - gw + nw - 1) / nw : 0;
+    const uint32_t data0 = smem_u32(smem) + (uint32_t)(warp * NST) * stage_bytes;
+    const int groups = (rows_total + RS - 1) / RS;
+    const int gw = blockIdx.x * GA_WARPS + warp, nw = gridDim.x * GA_WARPS;
+    const int n_my = groups > gw ? (groups - gw + nw - 1) / nw : 0;
 
     // source row (b*N + i) of this lane's row in the warp's j-th group; -1: index out of range (row of zeros), -2: no row
-    auto load_src = [&](long j) -> long {
-        const long row = (gw + j * nw) * RS + lane;
+    auto load_src = [&](int j) -> int {
+        const int row = (gw + j * nw) * RS + lane;
         if (j >= n_my || lane >= RS || row >= rows_total) return -2;
         long i = idx[row];
         if (i < 0) i += N;
         if (i < 0 || i >= N) return -1;
-        return (row / R) * N + i;
+        return (int)((unsigned)row / (unsigned)R) * N + (int)i;
     };
-    auto issue = [&](long j, long src) {
-        const int st = (int)(j % NST);
-        const uint32_t bar = bar0 + 8u * st, dst = data0 + (uint32_t)st * stage_bytes + (uint32_t)lane * row_bytes;
-        const unsigned valid = __ballot_sync(FULL, src >= 0);
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(valid) * row_bytes);
-        __syncwarp();
-        if (src >= 0) bulk_g2s(dst, points + (size_t)src * row_bytes, row_bytes, bar);
-        else if (src == -1) {
-            for (uint32_t o = 0; o < row_bytes; o += 16) sts_zero16(dst + o);
-            if (oob) *oob = 1;
+    auto issue = [&](int j, int st, int src) {                        // always commits one cp.async group (possibly empty)
+        if (j < n_my) {
+            const uint32_t dst = data0 + (uint32_t)st * stage_bytes;
+            if (src == -1 && oob) *oob = 1;
+            for (int r = 0; r < RS; ++r) {
+                const int sr = __shfl_sync(0xffffffffu, src, r);
+                if (sr != -2) warp_copy_row(dst + (uint32_t)r * row_bytes, sr >= 0 ? points + (size_t)sr * row_bytes : nullptr, row_bytes, lane);
+            }
         }
+        cp_async_commit();
     };
 
-    long pre[NST - 1];
+    int pre[NST - 1];
 #pragma unroll
     for (int p = 0; p < NST - 1; ++p) pre[p] = load_src(p);          // all index loads of the prologue are in flight together
 #pragma unroll
-    for (int p = 0; p < NST - 1; ++p)
-        if (p < n_my) issue(p, pre[p]);
-    long nxt = load_src(NST - 1);
-    for (long i = 0; i < n_my; ++i) {
-        const int st = (int)(i % NST);
-        mbar_wait(bar0 + 8u * st, (uint32_t)((i / NST) & 1));
-        fence_proxy_async();                                          // rows zero-filled by lanes are visible to the bulk store
+    for (int p = 0; p < NST - 1; ++p) issue(p, p, pre[p]);
+    int nxt = load_src(NST - 1);
+    int st = 0;                                                       // stage of group i; the refill goes to st - 1 (mod NST)
+    for (int i = 0; i < n_my; ++i) {
+        cp_async_wait<NST - 2>();                                     // group i has landed (this lane's share)
+        fence_proxy_async();                                          // ... and is visible to the bulk store
         __syncwarp();
         if (lane == 0) {
-            const long row0 = (gw + i * nw) * RS;
-            const long nrows = rows_total - row0 < RS ? rows_total - row0 : RS;
+            const int row0 = (gw + i * nw) * RS;
+            const int nrows = rows_total - row0 < RS ? rows_total - row0 : RS;
             bulk_s2g(out + (size_t)row0 * row_bytes, data0 + (uint32_t)st * stage_bytes, (uint32_t)nrows * row_bytes);
             bulk_commit();
+            bulk_wait_read<1>();                                      // the store committed one iteration ago has read its stage
         }
-        const long j = i + NST - 1;                                   // refill the stage whose store was committed one iteration ago
-        if (j < n_my) {
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-            issue(j, nxt);
-            nxt = load_src(j + 1);
-        }
+        __syncwarp();
+        issue(i + NST - 1, st == 0 ? NST - 1 : st - 1, nxt);          // ... which now takes the group NST-1 ahead
+        nxt = load_src(i + NST);
+        st = st + 1 == NST ? 0 : st + 1;
     }
     if (lane == 0) bulk_wait_all<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
 // three_interpolate: out[row, :] = (f[i0]*w0 + f[i1]*w1) + f[i2]*w2
-// A group = RS dense rows: 3*RS bulk loads, the (cleaned) weights ride in the stage header, the warp mixes one row
+// A group = RS dense rows: 3*RS row copies, the (cleaned) weights ride in the stage header, the warp mixes one row
 // per iteration from shared memory and stores it with coalesced 16-byte stores.
 // ---------------------------------------------------------------------------------------------
+constexpr int IN_WARPS = 8;
+
 __device__ __forceinline__ float rm_mix3(float a, float wa, float b, float wb, float c, float wc) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb)), __fmul_rn(c, wc));
 }
 
 template <int NST>
-__global__ void __launch_bounds__(RM_WARPS * 32, 1) interp_bulk_kernel(const char *__restrict__ feat, const int64_t *__restrict__ idx,
-                                                                       const float *__restrict__ w, int S, uint32_t row_bytes, int RS,
-                                                                       long N, long rows_total, float4 *__restrict__ out) {
+__global__ void __launch_bounds__(IN_WARPS * 32, 1) interp_async_kernel(const char *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                                        const float *__restrict__ w, int S, uint32_t row_bytes, int RS,
+                                                                        int N, int rows_total, float4 *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t head_bytes = 128;                                  // [RS*3] weights (RS <= 8 -> 96 bytes)
     const uint32_t stage_bytes = head_bytes + 3u * RS * row_bytes;
-    const uint32_t bar0 = ring_init<NST>(smem, warp, lane);
-    const uint32_t data0 = smem_u32(smem) + RM_BAR_AREA + (uint32_t)(warp * NST) * stage_bytes;
-    const long groups = (rows_total + RS - 1) / RS;
-    const long gw = (long)blockIdx.x * RM_WARPS + warp, nw = (long)gridDim.x * RM_WARPS;
-    const long n_my = groups > gw ? (groups - gw + nw - 1) / nw : 0;
+    const uint32_t data0 = smem_u32(smem) + (uint32_t)(warp * NST) * stage_bytes;
+    const int groups = (rows_total + RS - 1) / RS;
+    const int gw = blockIdx.x * IN_WARPS + warp, nw = gridDim.x * IN_WARPS;
+    const int n_my = groups > gw ? (groups - gw + nw - 1) / nw : 0;
     const int C4 = (int)(row_bytes >> 4);
+    const int lu = lane / 3, lj = lane - 3 * lu;                     // lane = 3*u + jn handles neighbour jn of the group's u-th row
 
-    // lane = 3*u + jn handles neighbour jn of the group's u-th row
-    struct Nb { long src; float wt; };
-    auto load_nb = [&](long j) -> Nb {
+    struct Nb { int src; float wt; };
+    auto load_nb = [&](int j) -> Nb {
         Nb nb; nb.src = -2; nb.wt = 0.f;
-        const long row = (gw + j * nw) * RS + lane / 3;
+        const int row = (gw + j * nw) * RS + lu;
         if (j >= n_my || lane >= 3 * RS || row >= rows_total) return nb;
-        long i = idx[row * 3 + lane % 3];
-        float wt = w[row * 3 + lane % 3];
+        long i = idx[(size_t)row * 3 + lj];
+        float wt = w[(size_t)row * 3 + lj];
         if ((unsigned long long)i >= (unsigned long long)S) {       // negative indices wrap once; still out of range: contributes nothing
             if (i < 0) i += S;
             if (i < 0 || i >= S) { i = 0; wt = 0.0f; }
         }
-        nb.src = (row / N) * S + i; nb.wt = wt;
+        nb.src = (int)((unsigned)row / (unsigned)N) * S + (int)i; nb.wt = wt;
         return nb;
     };
-    auto issue = [&](long j, const Nb &nb) {
-        const int st = (int)(j % NST);
-        const uint32_t bar = bar0 + 8u * st, base = data0 + (uint32_t)st * stage_bytes;
-        const unsigned valid = __ballot_sync(0xffffffffu, nb.src >= 0);
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(valid) * row_bytes);
-        __syncwarp();
-        if (nb.src >= 0) {
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * lane), "f"(nb.wt) : "memory");
-            bulk_g2s(base + head_bytes + (uint32_t)lane * row_bytes, feat + (size_t)nb.src * row_bytes, row_bytes, bar);
+    auto issue = [&](int j, int st, const Nb &nb) {
+        if (j < n_my) {
+            const uint32_t base = data0 + (uint32_t)st * stage_bytes;
+            if (nb.src >= 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * lane), "f"(nb.wt) : "memory");
+            const int n3 = 3 * RS;
+            for (int r = 0; r < n3; ++r) {
+                const int sr = __shfl_sync(0xffffffffu, nb.src, r);
+                if (sr >= 0) warp_copy_row(base + head_bytes + (uint32_t)r * row_bytes, feat + (size_t)sr * row_bytes, row_bytes, lane);
+            }
         }
+        cp_async_commit();
     };
 
-    Nb pre[NST];                                                     // all index / weight loads of the prologue are in flight together
+    Nb pre[NST - 1];                                                 // all index / weight loads of the prologue are in flight together
 #pragma unroll
-    for (int p = 0; p < NST; ++p) pre[p] = load_nb(p);
+    for (int p = 0; p < NST - 1; ++p) pre[p] = load_nb(p);
 #pragma unroll
-    for (int p = 0; p < NST; ++p)
-        if (p < n_my) issue(p, pre[p]);
-    Nb nxt = load_nb(NST);
-    for (long i = 0; i < n_my; ++i) {
-        const int st = (int)(i % NST);
+    for (int p = 0; p < NST - 1; ++p) issue(p, p, pre[p]);
+    Nb nxt = load_nb(NST - 1);
+    int st = 0;
+    for (int i = 0; i < n_my; ++i) {
+        // the stage consumed one iteration ago takes the group NST-1 ahead, before this group is waited for
+        issue(i + NST - 1, st == 0 ? NST - 1 : st - 1, nxt);
+        nxt = load_nb(i + NST);
+        cp_async_wait<NST - 1>();                                     // group i has landed (this lane's share)
+        __syncwarp();                                                 // ... every lane's share, and the weights in the header
         const uint32_t base = data0 + (uint32_t)st * stage_bytes;
-        mbar_wait(bar0 + 8u * st, (uint32_t)((i / NST) & 1));
-        __syncwarp();                                                 // the weights written by the other lanes are visible
-        const long row0 = (gw + i * nw) * RS;
-        const int nrows = (int)(rows_total - row0 < RS ? rows_total - row0 : RS);
+        const int row0 = (gw + i * nw) * RS;
+        const int nrows = rows_total - row0 < RS ? rows_total - row0 : RS;
+        float4 *orow = out + (size_t)row0 * C4;
 #pragma unroll 2
         for (int u = 0; u < nrows; ++u) {
             const float w0 = lds_f1(base + 12u * u), w1 = lds_f1(base + 12u * u + 4), w2 = lds_f1(base + 12u * u + 8);
@@ -201,119 +209,133 @@ __global__ void __launch_bounds__(RM_WARPS * 32, 1) interp_bulk_kernel(const cha
                 float4 o;
                 o.x = rm_mix3(a.x, w0, b.x, w1, c.x, w2); o.y = rm_mix3(a.y, w0, b.y, w1, c.y, w2);
                 o.z = rm_mix3(a.z, w0, b.z, w1, c.z, w2); o.w = rm_mix3(a.w, w0, b.w, w1, c.w, w2);
-                stg_stream(out + (size_t)(row0 + u) * C4 + col, o);
+                stg_stream(orow + (size_t)u * C4 + col, o);
             }
         }
         __syncwarp();                                                 // every lane is done reading the stage
-        const long j = i + NST;                                       // the same stage takes the group NST ahead
-        if (j < n_my) {
-            issue(j, nxt);
-            nxt = load_nb(j + 1);
-        }
+        st = st + 1 == NST ? 0 : st + 1;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // group_points: out[b, c, k, s] from rows gathered by idx[b, s, k]  (the Conv2d layout)
-// A unit = 32 consecutive centres s x a range of slots k.  Per slot: 32 bulk loads of feature rows into a padded tile
-// (row stride chosen so that 16-byte reads of 8 lanes hit 32 different banks), each lane then reads ITS row with
-// 16-byte shared loads and writes channel after channel; every store instruction is 128 contiguous bytes.  The unit's
-// index block is read once, coalesced, into shared memory.  xyz rows (12 bytes) are read through the LSU.
+// A unit = 32 consecutive centres s x a range of slots k.  Per slot: the 32 feature rows are copied by the whole warp
+// (coalesced) into a padded tile (row stride chosen so that 16-byte reads of 8 lanes hit 32 different banks); each lane
+// then reads ITS row with 16-byte shared loads and writes channel after channel: every store instruction is 128
+// contiguous bytes.  The unit's index block is read once, coalesced, into shared memory (as 32-bit row numbers b*N + i).
+// xyz rows (12 bytes) are read through the LSU.
 // ---------------------------------------------------------------------------------------------
+constexpr int GR_WARPS = 8;
+
 template <int NST>
-__global__ void __launch_bounds__(RM_WARPS * 32, 1) group_bulk_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
-                                                                      const char *__restrict__ feat, const int64_t *__restrict__ idx,
-                                                                      int N, int S, int K, int D, int xyz_first, int ksplit,
-                                                                      long units_total, float *__restrict__ out) {
+__global__ void __launch_bounds__(GR_WARPS * 32, 1) group_async_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                                                                       const char *__restrict__ feat, const int64_t *__restrict__ idx,
+                                                                       int N, int S, int K, int D, int xyz_first, int ksplit,
+                                                                       int units_total, float *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t row_bytes = (uint32_t)D * 4u;
     const uint32_t row_stride = row_bytes + (((D >> 2) & 1) ? 32u : 16u);     // (stride / 16) odd -> conflict-free 16-byte reads
     const uint32_t tile_bytes = 32u * row_stride;
     const int kper = (K + ksplit - 1) / ksplit;                       // slots per unit
-    const uint32_t idx_stride = (uint32_t)(kper + 1) * 8u;            // padded: 64-bit reads of a column are conflict-free
+    const uint32_t idx_stride = (uint32_t)(kper | 1) * 4u;            // odd number of words: column reads are conflict-free
     const uint32_t idx_bytes = (32u * idx_stride + 127u) & ~127u;
     const uint32_t warp_bytes = idx_bytes + NST * tile_bytes;
-    const uint32_t bar0 = ring_init<NST>(smem, warp, lane);
-    const uint32_t ibuf = smem_u32(smem) + RM_BAR_AREA + (uint32_t)warp * warp_bytes;
+    const uint32_t ibuf = smem_u32(smem) + (uint32_t)warp * warp_bytes;
     const uint32_t data0 = ibuf + idx_bytes;
-    const long gw = (long)blockIdx.x * RM_WARPS + warp, nw = (long)gridDim.x * RM_WARPS;
+    const int gw = blockIdx.x * GR_WARPS + warp, nw = gridDim.x * GR_WARPS;
     const int s_tiles = (S + 31) / 32;
     const int C = D + 3, xoff = xyz_first ? 0 : D, foff = xyz_first ? 3 : 0, D4 = D >> 2;
     const size_t cstride = (size_t)K * S;
-    uint32_t uses = 0;                                                // tiles issued so far by this warp (stage = uses % NST)
-    uint32_t done = 0;                                                // tiles consumed so far
+    // how the warp copies a tile: cpr 16-byte chunks per row; rpp rows per instruction when a row is < 512 bytes
+    const int cpr = (int)(row_bytes >> 4);
+    const int lanes_per_row = cpr >= 32 ? 32 : cpr;
+    const int rpp = 32 / lanes_per_row;
+    const int sub = lane / lanes_per_row, chunk = lane - sub * lanes_per_row;
 
-    for (long unit = gw; unit < units_total; unit += nw) {
-        const int kpart = (int)(unit % ksplit);
-        const long bt = unit / ksplit;
-        const int stile = (int)(bt % s_tiles), b = (int)(bt / s_tiles);
+    for (int unit = gw; unit < units_total; unit += nw) {
+        const int bt = unit / ksplit, kpart = unit - bt * ksplit;
+        const int b = bt / s_tiles, stile = bt - b * s_tiles;
         const int s0 = stile * 32, k0 = kpart * kper;
         const int nk = K - k0 < kper ? K - k0 : kper;
         const int s = s0 + lane;
         const bool live = s < S;
-        // ---- the unit's index block idx[b, s0..s0+31, k0..k0+nk) -> shared, coalesced over (s, k) ----
+        // ---- the unit's index block idx[b, s0..s0+31, k0..k0+nk) -> shared as row numbers b*N + i (-1: none) ----
         __syncwarp();
-        for (int e = lane; e < 32 * nk; e += 32) {
-            const int sl = e / nk, kk = e - sl * nk;
-            long r = -1;
-            if (s0 + sl < S) {
-                r = idx[((size_t)b * S + s0 + sl) * K + k0 + kk];
-                if (r < 0) r += N;
-                if (r >= N) r = -1;
+        {
+            int sl = 0, kk = lane;
+            while (kk >= nk) { kk -= nk; ++sl; }
+            while (sl < 32) {
+                int r = -1;
+                if (s0 + sl < S) {
+                    long i = idx[((size_t)b * S + s0 + sl) * K + k0 + kk];
+                    if (i < 0) i += N;
+                    if (i >= 0 && i < N) r = b * N + (int)i;
+                }
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ibuf + (uint32_t)sl * idx_stride + 4u * kk), "r"(r) : "memory");
+                kk += 32;
+                while (kk >= nk) { kk -= nk; ++sl; }
             }
-            asm volatile("st.shared.b64 [%0], %1;" ::"r"(ibuf + (uint32_t)sl * idx_stride + 8u * kk), "l"(r) : "memory");
         }
         __syncwarp();
-        auto my_row = [&](int kk) -> long {
-            long r;
-            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(ibuf + (uint32_t)lane * idx_stride + 8u * kk));
+        auto row_of = [&](int sl, int kk) -> int {
+            int r;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(ibuf + (uint32_t)sl * idx_stride + 4u * kk));
             return r;
         };
-        auto issue = [&](int kk) {
-            const int st = (int)(uses % NST);
-            const uint32_t bar = bar0 + 8u * st, dst = data0 + (uint32_t)st * tile_bytes + (uint32_t)lane * row_stride;
-            const long r = my_row(kk);
-            const unsigned valid = __ballot_sync(0xffffffffu, r >= 0);
-            if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(valid) * row_bytes);
-            __syncwarp();
-            if (r >= 0) bulk_g2s(dst, feat + ((size_t)b * N + r) * row_bytes, row_bytes, bar);
-            ++uses;
+        auto issue = [&](int kk, int st) {                            // always commits one cp.async group (possibly empty)
+            if (kk < nk) {
+                const uint32_t tile = data0 + (uint32_t)st * tile_bytes;
+                if (cpr >= 32) {
+                    for (int sl = 0; sl < 32; ++sl) {
+                        const int r = row_of(sl, kk);                 // broadcast read
+                        if (r >= 0) warp_copy_row(tile + (uint32_t)sl * row_stride, feat + (size_t)r * row_bytes, row_bytes, lane);
+                    }
+                } else {
+                    uint32_t dst = tile + (uint32_t)sub * row_stride + 16u * chunk;
+                    for (int sl = sub; sl < 32; sl += rpp, dst += rpp * row_stride) {   // rpp rows per instruction
+                        const int r = row_of(sl, kk);
+                        if (r >= 0) cp_async16(dst, feat + (size_t)r * row_bytes + 16u * chunk);
+                    }
+                }
+            }
+            cp_async_commit();
         };
         float cx = 0.f, cy = 0.f, cz = 0.f;
         if (live) {
             const float *cr = new_xyz + ((size_t)b * S + s) * 3;
             cx = cr[0]; cy = cr[1]; cz = cr[2];
         }
-        const int pro = nk < NST ? nk : NST;
-        for (int kk = 0; kk < pro; ++kk) issue(kk);
-        for (int kk = 0; kk < nk; ++kk) {
-            const long r = my_row(kk);
+#pragma unroll
+        for (int p = 0; p < NST - 1; ++p) issue(p, p);
+        int st = 0;
+        float *o = out + ((size_t)b * C * K + k0) * S + s;
+        for (int kk = 0; kk < nk; ++kk, o += S) {
+            issue(kk + NST - 1, st == 0 ? NST - 1 : st - 1);         // into the stage consumed one iteration ago
+            const int r = row_of(lane, kk);
             const bool ok = r >= 0;
-            float *o = out + ((size_t)b * C * K + (k0 + kk)) * S + s;
             // xyz channels through the LSU while the feature rows are (still) in flight
             if (live) {
-                const float *xr = xyz + ((size_t)b * N + (ok ? r : 0)) * 3;
+                const float *xr = xyz + (size_t)(ok ? r : 0) * 3;
                 __stcs(o + (size_t)(xoff + 0) * cstride, __fsub_rn(ok ? __ldg(xr + 0) : 0.0f, cx));
                 __stcs(o + (size_t)(xoff + 1) * cstride, __fsub_rn(ok ? __ldg(xr + 1) : 0.0f, cy));
                 __stcs(o + (size_t)(xoff + 2) * cstride, __fsub_rn(ok ? __ldg(xr + 2) : 0.0f, cz));
             }
-            const int st = (int)(done % NST);
-            mbar_wait(bar0 + 8u * st, (done / NST) & 1u);
+            cp_async_wait<NST - 1>();                                 // tile kk has landed (this lane's share)
+            __syncwarp();                                             // ... every lane's share
             const uint32_t rowa = data0 + (uint32_t)st * tile_bytes + (uint32_t)lane * row_stride;
             float *of = o + (size_t)foff * cstride;
             if (live) {
 #pragma unroll 4
-                for (int q = 0; q < D4; ++q) {
+                for (int q = 0; q < D4; ++q, of += 4 * cstride) {
                     const float4 v = ok ? lds_f4(rowa + 16u * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    __stcs(of + (size_t)(4 * q + 0) * cstride, v.x); __stcs(of + (size_t)(4 * q + 1) * cstride, v.y);
-                    __stcs(of + (size_t)(4 * q + 2) * cstride, v.z); __stcs(of + (size_t)(4 * q + 3) * cstride, v.w);
+                    __stcs(of, v.x); __stcs(of + cstride, v.y); __stcs(of + 2 * cstride, v.z); __stcs(of + 3 * cstride, v.w);
                 }
             }
-            ++done;
             __syncwarp();                                             // every lane is done reading the stage
-            if (kk + NST < nk) issue(kk + NST);
+            st = st + 1 == NST ? 0 : st + 1;
         }
+        cp_async_wait<0>();                                           // drain the (empty) tail groups before the ring restarts
     }
 }
 
@@ -336,28 +358,29 @@ static int dispatch_nst(int nst, F &&f) {
 }
 static int round_nst(int nst) { return nst >= 8 ? 8 : nst >= 6 ? 6 : nst >= 4 ? 4 : nst >= 3 ? 3 : 2; }
 
-// index_points through the bulk path.  Returns -100 when the shape does not qualify (caller falls back to gather.cu).
+// index_points through the asynchronous path.  Returns -100 when the shape does not qualify (caller falls back to gather.cu).
 int gather_bulk(const float *points, const int64_t *idx, int B, int N, int C, long R, float *out, int *oob, cudaStream_t st) {
     const uint32_t row_bytes = (uint32_t)C * 4u;
-    if (C % 4 != 0 || row_bytes < 128 || row_bytes > 48 * 1024) return -100;
+    if (C % 4 != 0 || row_bytes < 128 || row_bytes > 16 * 1024) return -100;
     if ((reinterpret_cast<uintptr_t>(points) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return -100;
     const long rows = (long)B * R;
+    if (rows >= (1L << 31) - 64 || (long)B * N >= (1L << 31) || R >= (1L << 31)) return -100;      // 32-bit row arithmetic in the kernel
     const int sms = sm_count();
     int rs_max = 32;
     while (rs_max > 1 && (size_t)rs_max * row_bytes > 16 * 1024) rs_max >>= 1;
-    const int RS = pick_rs(rows, rs_max, (long)sms * RM_WARPS);
+    const int RS = pick_rs(rows, rs_max, (long)sms * GA_WARPS);
     const size_t stage = (size_t)RS * row_bytes;
-    int nst = (int)((RM_SMEM_BUDGET - RM_BAR_AREA) / (RM_WARPS * stage));
-    if (nst < 2) return -100;
+    int nst = (int)(RM_SMEM_BUDGET / (GA_WARPS * stage));
+    if (nst < 3) return -100;
     nst = round_nst(nst);
     const long groups = (rows + RS - 1) / RS;
-    const int grid = (int)((groups + RM_WARPS - 1) / RM_WARPS < sms ? (groups + RM_WARPS - 1) / RM_WARPS : sms);
-    const size_t smem = RM_BAR_AREA + (size_t)RM_WARPS * nst * stage;
+    const int grid = (int)((groups + GA_WARPS - 1) / GA_WARPS < sms ? (groups + GA_WARPS - 1) / GA_WARPS : sms);
+    const size_t smem = (size_t)GA_WARPS * nst * stage;
     return dispatch_nst(nst, [&](auto tag) -> int {
-        constexpr int NST = decltype(tag)::value;
-        auto kern = gather_bulk_kernel<NST>;
+        constexpr int NST = decltype(tag)::value < 3 ? 3 : decltype(tag)::value;
+        auto kern = gather_async_kernel<NST>;
         B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, RM_WARPS * 32, smem, st>>>(reinterpret_cast<const char *>(points), idx, N, row_bytes, RS, R, rows,
+        kern<<<grid, GA_WARPS * 32, smem, st>>>(reinterpret_cast<const char *>(points), idx, N, row_bytes, RS, (int)R, (int)rows,
                                                 reinterpret_cast<char *>(out), oob);
         B200PC_LAUNCH_CHECK();
         return B200PC_OK;
@@ -366,25 +389,26 @@ int gather_bulk(const float *points, const int64_t *idx, int B, int N, int C, lo
 
 int interp_bulk(const float *feat, const int64_t *idx, const float *w, int B, int S, int N, int C, float *out, cudaStream_t st) {
     const uint32_t row_bytes = (uint32_t)C * 4u;
-    if (C % 4 != 0 || row_bytes < 256 || row_bytes > 8 * 1024) return -100;
+    if (C % 4 != 0 || row_bytes < 256 || row_bytes > 4 * 1024) return -100;
     if ((reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return -100;
     const long rows = (long)B * N;
+    if (rows >= (1L << 31) - 64 || (long)B * S >= (1L << 31)) return -100;      // 32-bit row arithmetic in the kernel
     const int sms = sm_count();
     int rs_max = 8;
-    while (rs_max > 1 && (size_t)3 * rs_max * row_bytes > 24 * 1024) rs_max >>= 1;
-    const int RS = pick_rs(rows, rs_max, (long)sms * RM_WARPS);
+    while (rs_max > 1 && (size_t)3 * rs_max * row_bytes > 12 * 1024) rs_max >>= 1;
+    const int RS = pick_rs(rows, rs_max, (long)sms * IN_WARPS);
     const size_t stage = 128 + (size_t)3 * RS * row_bytes;
-    int nst = (int)((RM_SMEM_BUDGET - RM_BAR_AREA) / (RM_WARPS * stage));
+    int nst = (int)(RM_SMEM_BUDGET / (IN_WARPS * stage));
     if (nst < 2) return -100;
     nst = round_nst(nst);
     const long groups = (rows + RS - 1) / RS;
-    const int grid = (int)((groups + RM_WARPS - 1) / RM_WARPS < sms ? (groups + RM_WARPS - 1) / RM_WARPS : sms);
-    const size_t smem = RM_BAR_AREA + (size_t)RM_WARPS * nst * stage;
+    const int grid = (int)((groups + IN_WARPS - 1) / IN_WARPS < sms ? (groups + IN_WARPS - 1) / IN_WARPS : sms);
+    const size_t smem = (size_t)IN_WARPS * nst * stage;
     return dispatch_nst(nst, [&](auto tag) -> int {
         constexpr int NST = decltype(tag)::value;
-        auto kern = interp_bulk_kernel<NST>;
+        auto kern = interp_async_kernel<NST>;
         B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, RM_WARPS * 32, smem, st>>>(reinterpret_cast<const char *>(feat), idx, w, S, row_bytes, RS, (long)N, rows,
+        kern<<<grid, IN_WARPS * 32, smem, st>>>(reinterpret_cast<const char *>(feat), idx, w, S, row_bytes, RS, N, (int)rows,
                                                 reinterpret_cast<float4 *>(out));
         B200PC_LAUNCH_CHECK();
         return B200PC_OK;
@@ -393,9 +417,12 @@ int interp_bulk(const float *feat, const int64_t *idx, const float *w, int B, in
 
 int group_bulk(const float *xyz, const float *new_xyz, const float *feat, const int64_t *idx, int B, int N, int S, int K, int D,
                int xyz_first, float *out, cudaStream_t st) {
-    if (D < 32 || D % 4 != 0 || D > 1024 || (reinterpret_cast<uintptr_t>(feat) & 15) || K > 256) return -100;
+    if (D < 16 || D % 4 != 0 || D > 1024 || (reinterpret_cast<uintptr_t>(feat) & 15) || K > 256) return -100;
+    const int cpr = D / 4;
+    if (cpr < 32 && 32 % cpr != 0) return -100;                        // rows shorter than 512 bytes must tile an instruction evenly
+    if ((long)B * N >= (1L << 31) || (long)B * ((S + 31) / 32) * K >= (1L << 31)) return -100;     // 32-bit row arithmetic in the kernel
     const int sms = sm_count();
-    const long warps = (long)sms * RM_WARPS;
+    const long warps = (long)sms * GR_WARPS;
     const long base_units = (long)B * ((S + 31) / 32);
     int ksplit = 1;
     while (ksplit < K && base_units * ksplit < 6 * warps) ksplit <<= 1;
@@ -404,18 +431,18 @@ int group_bulk(const float *xyz, const float *new_xyz, const float *feat, const 
     const long units = base_units * ksplit;
     const uint32_t row_stride = (uint32_t)D * 4u + (((D >> 2) & 1) ? 32u : 16u);
     const size_t tile = (size_t)32 * row_stride;
-    const size_t idx_bytes = ((size_t)32 * (kper + 1) * 8 + 127) & ~(size_t)127;
-    const size_t avail = (RM_SMEM_BUDGET - RM_BAR_AREA) / RM_WARPS;
+    const size_t idx_bytes = ((size_t)32 * (kper | 1) * 4 + 127) & ~(size_t)127;
+    const size_t avail = RM_SMEM_BUDGET / GR_WARPS;
     if (avail < idx_bytes + 2 * tile) return -100;
     const int nst = round_nst((int)((avail - idx_bytes) / tile));
-    const int grid = (int)((units + RM_WARPS - 1) / RM_WARPS < sms ? (units + RM_WARPS - 1) / RM_WARPS : sms);
-    const size_t smem = RM_BAR_AREA + (size_t)RM_WARPS * (idx_bytes + nst * tile);
+    const int grid = (int)((units + GR_WARPS - 1) / GR_WARPS < sms ? (units + GR_WARPS - 1) / GR_WARPS : sms);
+    const size_t smem = (size_t)GR_WARPS * (idx_bytes + nst * tile);
     return dispatch_nst(nst, [&](auto tag) -> int {
         constexpr int NST = decltype(tag)::value;
-        auto kern = group_bulk_kernel<NST>;
+        auto kern = group_async_kernel<NST>;
         B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, RM_WARPS * 32, smem, st>>>(xyz, new_xyz, reinterpret_cast<const char *>(feat), idx, N, S, K, D, xyz_first, ksplit,
-                                                units, out);
+        kern<<<grid, GR_WARPS * 32, smem, st>>>(xyz, new_xyz, reinterpret_cast<const char *>(feat), idx, N, S, K, D, xyz_first, ksplit,
+                                                (int)units, out);
         B200PC_LAUNCH_CHECK();
         return B200PC_OK;
     });
