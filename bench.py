@@ -15,6 +15,7 @@ CPU algorithm (oracle/ref_torch.py) timed on this box's host cores on a bounded 
 `--impl reference` times only that CPU path, on the same config, and prints the same line shape.
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -39,6 +40,13 @@ FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 x
 METRIC = "knn_point_gqueries_per_s"
 UNIT = "Gqueries/s"
 WORKLOAD = "C2: knn_point k=16, 16384 queries x 16384 refs, batch 8 per GPU, synthetic HDL-64 pairs"
+
+
+def bench_config(world):
+    """the `config` object, identical in the product arm and in the reference arm (the reference arm's bounded sample is
+    described in its cpu_baseline.sample / note)"""
+    return {"workload": WORKLOAD, "l2": "256 MB buffer rewritten before every timed step (L2 flush)",
+            "parallelism": "batch-sharded, %d x 8 frame pairs, no data-path collective" % world}
 
 
 def parse():
@@ -104,20 +112,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_knn_fn():
+    """-> (fn(ref [B,N,3], qry [B,S,3]) -> idx [B,S,k], kind).  kind "reference": the reference's OWN square_distance
+    (Utils/Pointnet2Utils.py:20-41, imported unmodified from the staged checkout oracle/_ref or /root/reference) followed
+    by the topk/permute expression of Group.forward (Utils/Layers.py:51-52); kind "port": oracle/ref_torch.py where no
+    checkout is available."""
+    from oracle import ref_loader, ref_torch
+    if ref_loader.available():
+        try:
+            sqd = ref_loader.pointnet2_utils().square_distance
+
+            def fn(ref, qry):
+                dist = sqd(ref, qry)                                                                  # Utils/Layers.py:51
+                return dist.topk(K_NN, dim=1, largest=False)[1].permute(0, 2, 1).contiguous()         # Utils/Layers.py:52
+            return fn, "reference"
+        except Exception as e:  # pragma: no cover
+            print("real reference not importable (%r): timing the port" % (e,), file=sys.stderr)
+    return (lambda ref, qry: ref_torch.knn_topk(K_NN, ref, qry)), "port"
+
+
 def cpu_reference_knn(a, b, reps, queries=NPTS):
-    """the reference's CPU algorithm for the step (square_distance + topk(dim=1), Utils/Layers.py:50-53)
-    on ONE frame pair (1/8 of the batch).  returns (Gq/s, seconds per call, threads)."""
-    from oracle import ref_torch
+    """the reference's CPU path for the step on ONE frame pair (1/8 of the batch).
+    returns (Gq/s, seconds per call, threads, kind)."""
+    fn, kind = reference_knn_fn()
     torch.set_num_threads(os.cpu_count() or 1)
     ref = torch.from_numpy(a[:1]); qry = torch.from_numpy(b[:1, :queries])
-    ref_torch.knn_topk(K_NN, ref[:, :2048], qry[:, :512])           # warm the thread pool
+    fn(ref[:, :2048], qry[:, :512])           # warm the thread pool
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        ref_torch.knn_topk(K_NN, ref, qry)
+        fn(ref, qry)
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
-    return queries / t / 1e9, t, torch.get_num_threads()
+    return queries / t / 1e9, t, torch.get_num_threads(), kind
 
 
 def run_reference(args, rank, world):
@@ -130,23 +157,24 @@ def run_reference(args, rank, world):
     queries = NPTS if args.steps + args.warmup <= 40 else 4096
     if args.ref_queries:
         queries = args.ref_queries
-    from oracle import ref_torch
+    fn, kind = reference_knn_fn()
     torch.set_num_threads(os.cpu_count() or 1)
     ref = torch.from_numpy(a); qry = torch.from_numpy(b[:, :queries])
     for _ in range(args.warmup):
-        ref_torch.knn_topk(K_NN, ref, qry)
+        fn(ref, qry)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ref_torch.knn_topk(K_NN, ref, qry)
+        fn(ref, qry)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     val = queries / dt / 1e9
-    sample = "1 of the 8 frame pairs per step: %d queries x %d refs, k=%d (torch CPU: dense [N,S] matrix + topk(dim=1))" % (
-        queries, NPTS, K_NN)
+    sample = "1 of the 8 frame pairs per step: %d queries x %d refs, k=%d (%s: dense [N,S] matrix + topk(dim=1))" % (
+        queries, NPTS, K_NN, "the reference's own torch-CPU code" if kind == "reference" else "torch-CPU port of the reference")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "config": bench_config(max(1, int(os.environ.get("WORLD_SIZE", "1")))),
+            "note": "reference arm: " + sample,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -168,6 +196,179 @@ def timed_steps(fn, steps, warmup, flush, stream_sync, barrier):
         evs.append((e0, e1))
     stream_sync(); barrier()
     return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3
+
+
+def bind_to_gpu_numa(dev):
+    """pin this process (and therefore its pinned host buffers, first-touched by it) to the CPUs local to the GPU's PCIe
+    root: eight ranks reading back indices at once otherwise share whatever node the launcher started them on.
+    Returns the cpulist string, or None where sysfs does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bdf
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-"); cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
+def e2e_bench(dev, a, b, steps, flush, barrier, dist):
+    """the C2 step through the host-buffer API (pinned host tensors in, pinned host indices out), three ways:
+      serial   - hostio.knn_point_host per step, int64 indices, every step ends before the next starts (round 1's number)
+      pipelined- hostio.KnnHostPipeline, int64: step i's read-back overlaps step i+1's upload + search (two streams);
+                 every step still uploads its inputs and reads its result back; timed over the whole loop
+      int32    - the same pipeline with the 32-bit index variant of the C ABI (half the read-back bytes)
+    -> seconds per step (max over ranks) for each"""
+    from b200pc import hostio
+    h_ref = torch.from_numpy(a).pin_memory(); h_qry = torch.from_numpy(b).pin_memory()
+    outs64 = [torch.empty(BATCH, NPTS, K_NN, dtype=torch.int64).pin_memory() for _ in range(2)]
+    outs32 = [torch.empty(BATCH, NPTS, K_NN, dtype=torch.int32).pin_memory() for _ in range(2)]
+    res = {}
+
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    secs = timed_steps(lambda: hostio.knn_point_host(K_NN, h_ref, h_qry, out=outs64[0], device=dev), steps, 3, flush,
+                       torch.cuda.synchronize, barrier)
+    res["serial"] = reduce_max(secs / steps)
+    for name, outs, dt in (("pipelined", outs64, torch.int64), ("int32", outs32, torch.int32)):
+        pipe = hostio.KnnHostPipeline(K_NN, device=dev, index_dtype=dt)
+        for i in range(3):
+            pipe.submit(h_ref, h_qry, outs[i % 2])
+        pipe.finish(); torch.cuda.synchronize(); barrier()
+        flush()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            pipe.submit(h_ref, h_qry, outs[i % 2])
+        pipe.finish()
+        e1.record(); torch.cuda.synchronize(); barrier()
+        res[name] = reduce_max(e0.elapsed_time(e1) / 1e3 / steps)
+    return res, int(h_ref.numel() * 4 + h_qry.numel() * 4), int(outs64[0].numel() * 8)
+
+
+def multi_gpu_lines(dev, rank, world, dist, flush, barrier):
+    """The two configurations of BASELINE.json that have an exchange step, timed on `world` ranks (max over ranks):
+      C5  PolyPCI.rebuild (PolyPCI/Models/Models_V1.py:102-114): 4 frames x (65536 queries x 65536 refs, K=1, return_nn),
+          queries sharded over the ranks, refs replicated, (index, neighbour) records all-gathered -- strong scaling.
+          Reported: search ms (no exchange), NCCL all_gather ms, and the peer-store variant where the producing kernel
+          writes its slab into every rank's symmetric buffer (no collective kernel).
+      C4  FlowNet3D training step (PointINet20230424/train_sceneflow.py:132-185): global batch 32 x 8192 points split over
+          the ranks, BatchNorm in train mode, Chamfer loss, backward, DDP gradient all-reduce, Adam -- strong scaling.
+    Also re-runs the query-sharded kNN / ball query of tests/test_gpu_dist.py and compares with the unsharded result."""
+    from b200pc import dist as bdist, ops, pointnet2_utils as P, synth
+    out = {"world": world}
+
+    def tmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(); barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize(); barrier()
+        return tmax(e0.elapsed_time(e1) / 1e3 / n)
+
+    # ---- C5 ----
+    F, NP = 4, 65536
+    fr = [synth.frame_pair(200 + i, NP) for i in range(F)]
+    refs = torch.from_numpy(np.stack([p[0] for p in fr])).to(dev)         # [4,65536,3] replicated on every rank
+    qry = torch.from_numpy(np.stack([p[1] for p in fr])).to(dev)
+    per = NP // world
+    mine = qry[:, rank * per:(rank + 1) * per].contiguous()
+    c5 = {"workload": "C5: PolyPCI.rebuild, 4 frames x 65536 queries x 65536 refs, K=1 + neighbour coordinates, query-sharded",
+          "scaling": "strong", "queries_per_rank": F * per, "record_bytes": 16,
+          "allgather_bytes_per_rank": F * per * 16, "allgather_bytes_total": F * NP * 16}
+    c5["search_ms"] = timed(lambda: ops.rebuild_pack(refs, mine, 0, ())) * 1e3
+    if world > 1:
+        c5["nccl_ms"] = timed(lambda: bdist.rebuild_sharded(refs, qry, mode="nccl")) * 1e3
+        c5["nccl_allgather_share_ms"] = c5["nccl_ms"] - c5["search_ms"]
+        full = ops.rebuild_pack(refs, qry, 0, ()) if rank == 0 else None
+        got = bdist.rebuild_sharded(refs, qry, mode="nccl")
+        ok = torch.equal(got.view(torch.int32), full.view(torch.int32)) if rank == 0 else True
+        try:
+            slab = bdist.PeerSlab(NP, F, dev)
+            c5["peer_ms"] = timed(lambda: bdist.rebuild_sharded(refs, qry, mode="peer", slab=slab)) * 1e3
+            c5["peer_exchange_share_ms"] = c5["peer_ms"] - c5["search_ms"]
+            gotp = bdist.rebuild_sharded(refs, qry, mode="peer", slab=slab)
+            okp = torch.equal(gotp.view(torch.int32), full.view(torch.int32)) if rank == 0 else True
+            c5["peer_identical_to_unsharded"] = bool(okp)
+        except Exception as e:
+            c5["peer_unavailable"] = repr(e)[:300]
+        c5["nccl_identical_to_unsharded"] = bool(ok)
+        c5["value_queries_per_s"] = F * NP / (min(c5["nccl_ms"], c5.get("peer_ms", 1e9)) / 1e3)
+    else:
+        c5["value_queries_per_s"] = F * NP / (c5["search_ms"] / 1e3)
+    out["c5_query_sharded"] = c5
+    del refs, qry, mine
+
+    # ---- tests/test_gpu_dist.py inside the bench: sharded == unsharded, bit for bit ----
+    if world > 1:
+        a, b = synth.batch_pairs(4, 1, 8192)
+        r = torch.from_numpy(a).to(dev); q = torch.from_numpy(b[:, :5001].copy()).to(dev)      # ragged shards
+        idx = bdist.query_sharded(lambda s: P.knn_point(16, r, s), q)
+        ball = bdist.query_sharded(lambda s: P.query_ball_point(1.0, 32, r, s), q)
+        ok = torch.equal(idx, P.knn_point(16, r, q)) and torch.equal(ball, P.query_ball_point(1.0, 32, r, q))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["query_sharded_check"] = "ok: sharded kNN / ball query identical to the unsharded call on every rank" if int(flag.item()) == 1 else "MISMATCH"
+
+    # ---- C4 ----
+    try:
+        from b200pc import pointinet, pytorch3d_shim as S3
+        GB, NP4 = 32, 8192
+        lb = GB // world
+        pa, pb = synth.batch_pairs(300 + rank * lb, lb, NP4)
+        p1 = torch.from_numpy(pa).to(dev).transpose(1, 2).contiguous(); p2 = torch.from_numpy(pb).to(dev).transpose(1, 2).contiguous()
+        f0 = torch.zeros(lb, 3, NP4, device=dev)
+        torch.manual_seed(0)
+        net = pointinet.FlowNet3D().train().to(dev)
+        model = net
+        if world > 1:
+            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index])
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+        def step(sync=True):
+            opt.zero_grad(set_to_none=True)
+            ctx = model.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+            with ctx:
+                flow = model(p1, p2, f0, f0)
+                loss, _ = S3.chamfer_distance((p1 + flow).permute(0, 2, 1), p2.permute(0, 2, 1))
+                loss.backward()
+            opt.step()
+
+        c4 = {"workload": "C4: FlowNet3D train step, global batch 32 x 8192 points, BatchNorm train mode, Chamfer loss, Adam",
+              "scaling": "strong", "global_batch": GB, "batch_per_rank": lb}
+        c4["step_ms"] = timed(lambda: step(True), n=5, warm=2) * 1e3
+        if world > 1:
+            c4["step_ms_without_allreduce"] = timed(lambda: step(False), n=5, warm=1) * 1e3
+            c4["allreduce_share_ms"] = c4["step_ms"] - c4["step_ms_without_allreduce"]
+            c4["gradient_bytes"] = int(sum(p.numel() for p in net.parameters() if p.requires_grad) * 4)
+        c4["value_pairs_per_s"] = GB / (c4["step_ms"] / 1e3)
+        out["c4_ddp"] = c4
+    except Exception as e:  # pragma: no cover
+        out["c4_ddp"] = {"error": repr(e)[:300]}
+    return out
 
 
 def extras(dev, a, b, flush):
@@ -322,6 +523,33 @@ def pointinet_bench(dev, rank, steps, flush, barrier, dist):
         if dist is not None:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         out[name] = float(tm.item())
+    # the UNMODIFIED upstream PointINet (PointINet20230424/models/models.py:79-125, staged under oracle/_ref by
+    # oracle/make_ref.py) on the CUDA ops through b200pc.dropin: eager, like the reference's own test.py calls it
+    ref_dir = os.path.join(ROOT, "oracle", "_ref", "PointINet20230424")
+    if not os.path.isdir(ref_dir):
+        ref_dir = "/root/reference/PointINet20230424"
+    if os.path.isdir(os.path.join(ref_dir, "models")):
+        from b200pc import dropin
+        try:
+            up = dropin.import_reference(ref_dir, "models.models")
+            torch.manual_seed(0)
+            rnet = up.PointINet(freeze=1).eval().to(dev)
+
+            def real_eager():
+                with torch.no_grad():
+                    rnet(*dev_in)
+
+            torch.manual_seed(3000 + rank)
+            secs = timed_steps(real_eager, steps, 3, flush, torch.cuda.synchronize, barrier)
+            tm = torch.tensor([secs / steps], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            out["real_dropin_eager"] = float(tm.item())
+            del rnet
+        except Exception as e:  # pragma: no cover
+            print("real-reference drop-in measurement failed: %r" % (e,), file=sys.stderr)
+        finally:
+            dropin.uninstall()
     if dist is None:
         # throughput mode, one GPU only: 8 frame pairs per replay (FPS runs 8 clusters side by side, PointsFusion's
         # per-item loop collapses into batched searches).  Not the C1 configuration (batch 1).
@@ -377,6 +605,7 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    numa = bind_to_gpu_numa(dev) if world > 1 else None       # before any pinned buffer is allocated
     # every rank owns its own 8 frame pairs (weak scaling, batch sharding: no exchange in the path)
     a, b = synth.batch_pairs(rank * BATCH, BATCH, NPTS)
     ref = torch.from_numpy(a).to(dev); qry = torch.from_numpy(b).to(dev)
@@ -397,6 +626,25 @@ def main():
     secs = timed_steps(lambda: P.knn_point(K_NN, ref, qry), args.steps, args.warmup, flush, torch.cuda.synchronize, barrier)
     abi_calls = ops.launch_count
     clocks = sampler.stop() if rank == 0 else None
+    # sustained rate: the same call back to back for >= 2 s (no flush in between: the kernel reads 3 MB, it is not
+    # memory bound), clocks sampled over that window
+    sustained = None
+    if args.extras:
+        n_sus = int(max(200, min(6000, 2.0 / max(secs / args.steps, 1e-4))))
+        sampler2 = ClockSampler(gpu_id)
+        if rank == 0:
+            sampler2.start()
+        torch.cuda.synchronize(); barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_sus):
+            P.knn_point(K_NN, ref, qry)
+        e1.record(); torch.cuda.synchronize(); barrier()
+        sus = torch.tensor([e0.elapsed_time(e1) / 1e3 / n_sus], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(sus, op=dist.ReduceOp.MAX)
+        sustained = {"ms_per_step": float(sus.item()) * 1e3, "steps": n_sus, "value": BATCH * NPTS * world / float(sus.item()) / 1e9,
+                     "clocks": sampler2.stop() if rank == 0 else None}
     tmax = torch.tensor([secs], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -404,23 +652,18 @@ def main():
     queries_per_step = BATCH * NPTS * world
     value = queries_per_step * args.steps / secs_max / 1e9
 
-    # ---- end to end: pinned host inputs -> H2D -> knn_point -> D2H of the indices -------------
-    h_ref = torch.from_numpy(a).pin_memory(); h_qry = torch.from_numpy(b).pin_memory()
-    h_out = torch.empty(BATCH, NPTS, K_NN, dtype=torch.int64).pin_memory()
-
-    from b200pc import hostio
-
-    def e2e_step():
-        # public host-buffer API: H2D of the inputs, search, D2H of the int64 indices, all inside the timed region
-        # (chunks="auto": C2 is one resident wave of the search kernel, so it is NOT split into double-buffered chunks)
-        hostio.knn_point_host(K_NN, h_ref, h_qry, out=h_out, device=dev)
-
+    # ---- end to end: pinned host inputs -> H2D -> knn_point -> D2H of the indices, every step ---
     e2e_steps = max(3, min(args.steps, 50))
-    esecs = timed_steps(e2e_step, e2e_steps, 3, flush, torch.cuda.synchronize, barrier)
-    et = torch.tensor([esecs], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    e2e_value = queries_per_step * e2e_steps / float(et.item()) / 1e9
+    e2e_res, h2d_bytes, d2h_bytes = e2e_bench(dev, a, b, e2e_steps, flush, barrier, dist)
+    e2e_value = queries_per_step / e2e_res["pipelined"] / 1e9
+
+    # ---- the configurations with an exchange step (C5 all-gather, C4 DDP) on these `world` ranks ----
+    multi = None
+    if args.extras:
+        try:
+            multi = multi_gpu_lines(dev, rank, world, dist, flush, barrier)
+        except Exception as e:  # pragma: no cover
+            multi = {"error": repr(e)[:300]}
 
     # ---- metric (i): PointINet frames/s, every rank on its own frame pairs ----------------------
     pn = None
@@ -459,18 +702,21 @@ def main():
                         "traffic is 3.7 MB against 17.2 GFLOP"}
 
     # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
-    cval, csec, cthreads = cpu_reference_knn(a, b, reps=3)
-    cpu_baseline = {"value": cval, "unit": UNIT, "cores": cthreads, "kind": "port",
+    cval, csec, cthreads, ckind = cpu_reference_knn(a, b, reps=3)
+    cpu_baseline = {"value": cval, "unit": UNIT, "cores": cthreads, "kind": ckind,
                     "sample": "1 of the 8 frame pairs (16384 q x 16384 refs, k=16), median of 3; %.2f s per call" % csec}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "256 MB buffer rewritten before every timed step (L2 flush)",
-                       "parallelism": "batch-sharded, %d x 8 frame pairs, no data-path collective" % world},
+            "config": bench_config(world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_ref.numel() * 4 + h_qry.numel() * 4),
-                    "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps,
+                    "api": "b200pc.hostio.KnnHostPipeline (int64 indices like the reference; step i's read-back overlaps step i+1's upload and search)",
+                    "serial_value": queries_per_step / e2e_res["serial"] / 1e9,
+                    "int32_value": queries_per_step / e2e_res["int32"] / 1e9, "int32_d2h_bytes_per_step": d2h_bytes // 2,
+                    "numa_cpulist": numa},
             # pack_refs_kernel + search_kernel per knn_point call (no ref split at C2), timed steps only
             "gpu_launches": int(args.steps * 2), "abi_calls_incl_warmup": int(abi_calls),
             "roofline": roofline, "cpu_baseline": cpu_baseline}
@@ -480,6 +726,11 @@ def main():
                              "ms_per_frame": pn["graph"] * 1e3, "ms_per_frame_e2e": pn["graph_e2e"] * 1e3, "ms_per_frame_eager": pn["eager"] * 1e3,
                              "note": "value/e2e_value: forward captured as one CUDA graph (RNG tape, folded BatchNorm); eager_value: per-op dispatch like the reference",
                              "paper_rtx2060_frames_per_s": 4.9}
+        if "real_dropin_eager" in pn:
+            line["pointinet"]["real_dropin_eager_value"] = world / pn["real_dropin_eager"]
+            line["pointinet"]["ms_per_frame_real_dropin_eager"] = pn["real_dropin_eager"] * 1e3
+            line["pointinet"]["real_dropin_note"] = ("the reference's own PointINet20230424/models/models.py, unmodified, on the CUDA ops via "
+                                                     "b200pc.dropin.install() (eager, per-op dispatch through torch.ops.b200pc.*)")
         if "graph_batch8_per_frame" in pn:
             line["pointinet"]["batch8_frames_per_s"] = 1.0 / pn["graph_batch8_per_frame"]
             line["pointinet"]["batch8_note"] = "throughput mode, NOT the C1 configuration: 8 frame pairs per graph replay on one GPU"
@@ -490,6 +741,10 @@ def main():
                                                      "sample": "one forward, %.1f s" % csec}
             except Exception as e:  # pragma: no cover
                 line["pointinet"]["cpu_baseline"] = {"error": repr(e)}
+    if sustained:
+        line["sustained"] = sustained
+    if multi:
+        line["extra_multi"] = multi
     if args.extras and world == 1:
         try:
             line["extra"] = extras(dev, a, b, flush)

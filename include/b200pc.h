@@ -72,6 +72,11 @@ int b200pc_square_distance(const float *src, const float *dst, int B, int N, int
 int b200pc_knn(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
                float *dist, void *workspace, size_t workspace_bytes, b200pc_stream_t stream);
 
+/* The same search with 32-bit indices (N < 2^31 always holds): for host-buffer callers that read the result back over
+ * PCIe -- half the bytes of the int64 form the reference's tensors use.  Same order, same ties, -1 for unfilled slots. */
+int b200pc_knn_i32(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx, float *dist,
+                   void *workspace, size_t workspace_bytes, b200pc_stream_t stream);
+
 /* ---- a2: query_ball_point(radius, nsample, xyz, new_xyz)  Utils/Pointnet2Utils.py:88-108 -- */
 /* r2 = (float)(radius*radius) computed in double by the caller.  idx [B,S,nsample] int64:
  * the nsample lowest-index refs with NOT(d > r2), padded with the first; N if the ball is empty. */
@@ -154,6 +159,20 @@ int b200pc_group_points_bwd(const float *grad_out, const int64_t *idx, int B, in
  * workspace: b200pc_search_workspace_bytes(B, N, S, k).                                           */
 int b200pc_fusion_group(const float *qry, const float *ref, const float *feat, int B, int N, int S, int k, int Cf,
                         float *resi, float *nn, float *gfeat, int64_t *idx, void *workspace, size_t workspace_bytes,
+                        b200pc_stream_t stream);
+
+/* ---- a8 at C5: PolyPCI.rebuild for a QUERY SHARD  PolyPCI/Models/Models_V1.py:102-114 ------------------------------- */
+/* knn_points(qry, ref, K=1, return_nn=True) for the S_local queries of this rank (queries [s_offset, s_offset+S_local) of
+ * S_total), packed as 16-byte records {bit pattern of the int32 index, x, y, z} in s-major order:
+ *   local_out [S_local, B, 4] fp32 (may be NULL);
+ *   peer_out[p] (p < n_peers <= 8): base of a [S_total, B, 4] buffer of rank p, mapped into this process (symmetric /
+ *   peer memory); this rank's slab [s_offset, s_offset+S_local) is written into every one of them by the same kernel,
+ *   so the all-gather of the shard outputs needs no separate collective -- the ranks meet at a barrier afterwards.
+ * With n_peers == 0 the records stay local (single GPU, or an NCCL all_gather of local_out by the caller).
+ * peer_out is a HOST array of device pointers.  workspace: b200pc_rebuild_pack_workspace_bytes().                    */
+size_t b200pc_rebuild_pack_workspace_bytes(int B, int N, int S_local);
+int b200pc_rebuild_pack(const float *ref, const float *qry, int B, int N, int S_local, int s_offset, float *local_out,
+                        void *const *peer_out, int n_peers, void *workspace, size_t workspace_bytes,
                         b200pc_stream_t stream);
 
 /* ---- f4: PolyPCI polynomial fit + evaluation  ---------------------------

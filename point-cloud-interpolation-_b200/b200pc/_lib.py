@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200pc_fps_workspace_bytes": (_z, [_i, _i]),
     "b200pc_square_distance": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "b200pc_knn": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
+    "b200pc_knn_i32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "b200pc_ball_query": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p, _z, _p]),
     "b200pc_three_nn": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "b200pc_three_interpolate": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
@@ -35,6 +36,8 @@ SIGNATURES = {
     "b200pc_feature_propagation_workspace_bytes": (_z, [_i, _i, _i]),
     "b200pc_feature_propagation": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "b200pc_fusion_group": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "b200pc_rebuild_pack_workspace_bytes": (_z, [_i, _i, _i]),
+    "b200pc_rebuild_pack": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _z, _p]),
     "b200pc_fps": (_i, [_p, _i, _i, _i, _p, _p, _p, _z, _p]),
     "b200pc_fps_sample": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "b200pc_gather": (_i, [_p, _p, _i, _i, _i, _l, _p, _p, _p]),

@@ -56,3 +56,49 @@ def query_sharded(op, queries, group=None):
     if isinstance(out, tuple):
         return tuple(all_gather_rows(o, S, 1, group) if o is not None else None for o in out)
     return all_gather_rows(out, S, 1, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# C5: PolyPCI.rebuild (K=1 nearest neighbour + its coordinates) query-sharded over the ranks
+# ------------------------------------------------------------------------------------------------
+class PeerSlab:
+    """A [S_total, B, 4] fp32 buffer on every rank, allocated as torch symmetric memory and rendezvoused over the group:
+    every rank holds the base pointers of all its peers' copies, so a kernel can store its shard of records straight
+    into every peer over NVLink (`b200pc_rebuild_pack`) -- the all-gather needs no collective launch, only a barrier."""
+
+    def __init__(self, s_total, batch, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty((int(s_total), int(batch), 4), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def barrier(self):
+        self.hdl.barrier()
+
+
+def rebuild_sharded(refs, queries, mode="nccl", slab=None, group=None):
+    """`PolyPCI.rebuild` (PolyPCI/Models/Models_V1.py:102-114) with the queries sharded over the ranks and the refs
+    replicated: every rank searches S/world queries and the (index, neighbour) records are assembled on every rank.
+      mode "nccl": ONE all_gather_into_tensor of the [S/world, B, 4] record slabs (16 bytes per query);
+      mode "peer": the producing kernel stores its slab into every rank's symmetric buffer (`slab`, a PeerSlab),
+                   followed by one symmetric-memory barrier -- no collective kernel at all.
+    S must divide evenly (C5: 65 536 / 8).  Returns the assembled records [S,B,4] (ops.unpack_rebuild splits them)."""
+    from . import ops
+    world = dist.get_world_size(group); rank = dist.get_rank(group)
+    B, S, _ = queries.shape
+    if S % world:
+        raise ValueError("rebuild_sharded: %d queries do not divide over %d ranks (use query_sharded for ragged shards)" % (S, world))
+    per = S // world
+    mine = queries[:, rank * per:(rank + 1) * per].contiguous()
+    if mode == "peer":
+        slab.barrier()                                   # every peer is done reading the previous contents
+        ops.rebuild_pack(refs, mine, s_offset=rank * per, peer_ptrs=slab.ptrs)
+        slab.barrier()                                   # every peer's stores have landed
+        return slab.buf
+    local = ops.rebuild_pack(refs, mine, s_offset=0, peer_ptrs=())
+    out = torch.empty(S, B, 4, dtype=torch.float32, device=queries.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out

@@ -300,3 +300,36 @@ def install(reference_modules=("Utils.Pointnet2Utils", "models.pointnet2_utils")
                         _set(other, "knn_group_withI", new_fn)
             patched.append(lname)
     return patched
+
+
+def import_reference(root, module, extra_stubs=("emd", "open3d", "wandb")):
+    """Import one of the reference's own modules from a checkout at `root` (e.g. ".../PointINet20230424" + "models.models",
+    or the repository root + "Models.New_Models0") with the drop-in active.  The reference does not import on a stock
+    Python 3.12 image: Utils/Pointnet2Utils.py:1 needs lib2to3, Utils/Utils.py:10 the `emd` extension, the datasets and
+    visualisers open3d / wandb -- all unused by the hot path; empty placeholder modules are registered for those that are
+    not installed.  Models/*.py:11 set CUDA_LAUNCH_BLOCKING at import; the caller's value is restored."""
+    import os
+    for name in extra_stubs:
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                _ensure_stub(name)
+    install_pytorch3d()
+    if "lib2to3.pgen2.token" not in sys.modules:
+        try:
+            importlib.import_module("lib2to3.pgen2.token")
+        except Exception:
+            _ensure_stub("lib2to3"); _ensure_stub("lib2to3.pgen2"); _ensure_stub("lib2to3.pgen2.token", NAME=1)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    blocking = os.environ.get("CUDA_LAUNCH_BLOCKING")
+    try:
+        mod = importlib.import_module(module)
+    finally:
+        if blocking is None:
+            os.environ.pop("CUDA_LAUNCH_BLOCKING", None)
+        else:
+            os.environ["CUDA_LAUNCH_BLOCKING"] = blocking
+    install()
+    return mod

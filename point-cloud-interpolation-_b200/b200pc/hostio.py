@@ -53,11 +53,50 @@ def _pipelined(op, host_inputs, host_out, device, chunks):
 
 
 def knn_point_host(nsample, xyz, new_xyz, out=None, device="cuda", chunks="auto"):
-    """knn_point on pinned HOST tensors xyz [B,N,3], new_xyz [B,S,3] -> pinned host int64 [B,S,nsample].
+    """knn_point on pinned HOST tensors xyz [B,N,3], new_xyz [B,S,3] -> pinned host int64 [B,S,nsample]
+    (int32 when `out` is an int32 tensor: half the bytes over PCIe, same values).
     The copy into `out` is asynchronous: synchronise the device's current stream before reading it."""
     if out is None:
         out = torch.empty(xyz.shape[0], new_xyz.shape[1], nsample, dtype=torch.int64).pin_memory()
+    if out.dtype == torch.int32:
+        from . import ops
+        return _pipelined(lambda r, q: ops.knn_search_i32(r, q, nsample, ops.FORM_REF_NORM_FIRST), [xyz, new_xyz], out, device, chunks)
     return _pipelined(lambda r, q: P.knn_point(nsample, r, q), [xyz, new_xyz], out, device, chunks)
+
+
+class KnnHostPipeline:
+    """Back-to-back host-buffer searches with the copies of consecutive CALLS overlapped: call i's read-back (the
+    expensive part: indices over PCIe) runs on one stream while call i+1's upload and search run on the other.
+    Every call still does its own H2D of the inputs and D2H of its result; `submit` returns immediately and
+    `finish` joins both streams into the caller's current stream.  Buffers are per slot (two calls in flight)."""
+
+    def __init__(self, nsample, device="cuda", index_dtype=torch.int64):
+        self.k = int(nsample)
+        self.device = torch.device(device)
+        self.streams = _streams(self.device, 2)
+        self.dtype = index_dtype
+        self.calls = 0
+
+    def submit(self, xyz, new_xyz, out):
+        from . import ops
+        s = self.streams[self.calls % 2]
+        if self.calls < 2:
+            s.wait_stream(torch.cuda.current_stream(self.device))
+        self.calls += 1
+        with torch.cuda.stream(s):
+            r = xyz.to(self.device, non_blocking=True); q = new_xyz.to(self.device, non_blocking=True)
+            if self.dtype == torch.int32:
+                idx = ops.knn_search_i32(r, q, self.k, ops.FORM_REF_NORM_FIRST)
+            else:
+                idx = P.knn_point(self.k, r, q)
+            out.copy_(idx, non_blocking=True)
+        return out
+
+    def finish(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+        self.calls = 0
 
 
 def query_ball_point_host(radius, nsample, xyz, new_xyz, out=None, device="cuda", chunks="auto"):

@@ -86,6 +86,7 @@ OP_SCHEMAS = {
     # op name == C entry point without the b200pc_ prefix (tests/test_abi.py keeps the two lists in step)
     "square_distance": "(Tensor src, Tensor dst) -> Tensor",
     "knn": "(Tensor ref, Tensor qry, int k, int form, bool want_dist) -> (Tensor, Tensor)",
+    "knn_i32": "(Tensor ref, Tensor qry, int k, int form) -> Tensor",
     "ball_query": "(Tensor xyz, Tensor new_xyz, float r2, int nsample) -> Tensor",
     "fps": "(Tensor xyz, int npoint, Tensor start) -> Tensor",
     "fps_sample": "(Tensor xyz, int npoint, Tensor start) -> (Tensor, Tensor)",
@@ -98,6 +99,7 @@ OP_SCHEMAS = {
     "three_interpolate_bwd": "(Tensor gout, Tensor feat, Tensor idx, Tensor weight, bool want_gweight) -> (Tensor, Tensor)",
     "feature_propagation": "(Tensor unknown, Tensor known, Tensor feat, int variant) -> (Tensor, Tensor, Tensor)",
     "fusion_group": "(Tensor qry, Tensor ref, Tensor? feat, int k) -> (Tensor, Tensor, Tensor, Tensor)",
+    "rebuild_pack": "(Tensor ref, Tensor qry, int s_offset, int[] peer_ptrs) -> Tensor",
     "chamfer_fwd": "(Tensor x, Tensor y) -> (Tensor, Tensor, Tensor, Tensor, Tensor)",
     "chamfer_bwd": "(Tensor x, Tensor y, Tensor ix, Tensor iy, Tensor gloss) -> (Tensor, Tensor)",
     "poly_predict": "(Tensor[] frames, Tensor weights) -> Tensor",
@@ -148,6 +150,18 @@ def _knn(ref, qry, k, form, want_dist):
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_knn, _ptr(ref), _ptr(qry), B, N, S, k, int(form), _ptr(idx), _ptr(dist), _ptr(ws), nws, _stream(dev))
     return idx, (dist if want_dist else _f32(B, S, 0, like=ref))
+
+
+@_register("knn_i32", lambda ref, qry, k, form: torch.empty(qry.shape[0], qry.shape[1], k, dtype=torch.int32, device=ref.device))
+def _knn_i32(ref, qry, k, form):
+    B, N, _ = ref.shape; S = qry.shape[1]
+    dev = ref.device
+    idx = torch.empty(B, S, k, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    nws = lib.b200pc_search_workspace_bytes(B, N, S, k)
+    ws = _workspace(nws, dev)
+    _call(dev, lib.b200pc_knn_i32, _ptr(ref), _ptr(qry), B, N, S, k, int(form), _ptr(idx), C.c_void_p(0), _ptr(ws), nws, _stream(dev))
+    return idx
 
 
 # ---- a2 ----------------------------------------------------------------------------------
@@ -397,6 +411,23 @@ def _fusion_group(qry, ref, feat, k):
     return resi, nn, gf, idx
 
 
+@_register("rebuild_pack", lambda ref, qry, s_offset, peer_ptrs: _f32(qry.shape[1], qry.shape[0], 4, like=ref))
+def _rebuild_pack(ref, qry, s_offset, peer_ptrs):
+    """PolyPCI.rebuild for a query shard: K=1 search + (index, neighbour xyz) records [S_local,B,4]; the same kernel also
+    stores the slab into every peer buffer (symmetric memory base pointers) -- the all-gather without a collective."""
+    B, N, _ = ref.shape; S = qry.shape[1]
+    dev = ref.device
+    out = _f32(S, B, 4, like=ref)
+    lib = _lib.load()
+    nws = lib.b200pc_rebuild_pack_workspace_bytes(B, N, S)
+    ws = _workspace(nws, dev)
+    n = len(peer_ptrs)
+    arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    _call(dev, lib.b200pc_rebuild_pack, _ptr(ref), _ptr(qry), B, N, S, int(s_offset), _ptr(out), arr if n else C.c_void_p(0), n,
+          _ptr(ws), nws, _stream(dev))
+    return out
+
+
 # ---- a9 ----------------------------------------------------------------------------------
 def _chamfer_fake(x, y):
     B, N, M = x.shape[0], x.shape[1], y.shape[1]
@@ -474,6 +505,15 @@ def knn_search(ref, qry, k, form, want_dist=False):
         raise RuntimeError("selected index k out of range (k=%d > %d reference points)" % (k, ref.shape[1]))
     idx, dist = _O.knn(ref, qry, k, int(form), bool(want_dist))
     return (idx, dist) if want_dist else idx
+
+
+def knn_search_i32(ref, qry, k, form):
+    """knn_search with int32 indices [B,S,k] (host-buffer callers: half the read-back bytes of the reference's int64)."""
+    ref = _prep(ref, "ref"); qry = _prep(qry, "qry")
+    k = int(k)
+    if k > ref.shape[1]:
+        raise RuntimeError("selected index k out of range (k=%d > %d reference points)" % (k, ref.shape[1]))
+    return _O.knn_i32(ref, qry, k, int(form))
 
 
 def ball_query(radius, nsample, xyz, new_xyz):
@@ -580,6 +620,20 @@ def fusion_group(qry, ref, k, feat=None):
         if feat.shape[2] == 0:
             feat = None
     return _O.fusion_group(qry, ref, feat, k)
+
+
+def rebuild_pack(ref, qry, s_offset=0, peer_ptrs=()):
+    """PolyPCI.rebuild (PolyPCI/Models/Models_V1.py:102-114) on point-major inputs for a query shard: ref [B,N,3],
+    qry [B,S_local,3] -> records [S_local,B,4] = {int32 index bits, nn x, y, z}; `peer_ptrs`: base addresses of the ranks'
+    [S_total,B,4] symmetric buffers, written by the same kernel at row offset `s_offset`."""
+    return _O.rebuild_pack(_prep(ref, "ref"), _prep(qry, "qry"), int(s_offset), [int(p) for p in peer_ptrs])
+
+
+def unpack_rebuild(records):
+    """records [S,B,4] -> (idx [B,S] int64, nn [B,S,3])"""
+    idx = records[..., 0].contiguous().view(torch.int32).long().transpose(0, 1).contiguous()
+    nn = records[..., 1:4].transpose(0, 1).contiguous()
+    return idx, nn
 
 
 def chamfer(x, y):

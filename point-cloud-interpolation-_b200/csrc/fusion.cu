@@ -46,9 +46,75 @@ __global__ void __launch_bounds__(256) fusion_features_kernel(const float *__res
     }
 }
 
+// PolyPCI.rebuild (PolyPCI/Models/Models_V1.py:102-114) for a query shard: nearest neighbour + its coordinates as ONE
+// 16-byte record {index bits, x, y, z} per query, stored s-major ([S_total, B, 4]) so that the shards of the ranks are
+// contiguous slabs.  The same thread stores the record into the local buffer and into every peer's buffer (peer-mapped
+// symmetric memory: plain st.global over NVLink), i.e. the all-gather of the shard outputs happens from inside the
+// producing kernel -- no separate collective launch; the ranks only meet at a barrier afterwards.
+constexpr int MAX_PEERS = 8;
+struct PeerPtrs { float4 *p[MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) rebuild_pack_kernel(const float *__restrict__ ref, const int32_t *__restrict__ idx, int B, int N,
+                                                           int S_local, int s_offset, float4 *__restrict__ local_out,
+                                                           PeerPtrs peers, int n_peers) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;      // e = s * B + b : the record's position inside the shard slab
+    if (e >= (long)S_local * B) return;
+    const int s = (int)(e / B), b = (int)(e - (long)s * B);
+    const int i = idx[(size_t)b * S_local + s];
+    float4 rec;
+    rec.x = __int_as_float(i);
+    if (i >= 0 && i < N) {
+        const float *r = ref + ((size_t)b * N + i) * 3;
+        rec.y = __ldg(r + 0); rec.z = __ldg(r + 1); rec.w = __ldg(r + 2);
+    } else {
+        rec.y = rec.z = rec.w = __int_as_float(0x7fc00000);
+    }
+    if (local_out) local_out[e] = rec;
+    const size_t g = (size_t)s_offset * B + e;
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+        if (p < n_peers) peers.p[p][g] = rec;
+}
+
 }  // namespace b200pc
 
 using namespace b200pc;
+
+namespace b200pc {
+int run_topk_i32(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx32, float *dist,
+                 void *ws, size_t ws_bytes, cudaStream_t st);
+}
+
+extern "C" size_t b200pc_rebuild_pack_workspace_bytes(int B, int N, int S_local) {
+    if (B <= 0 || N <= 0 || S_local <= 0) return 256;
+    return align_up(b200pc_search_workspace_bytes(B, N, S_local, 1), 256) + align_up((size_t)B * S_local * sizeof(int32_t), 256);
+}
+
+extern "C" int b200pc_rebuild_pack(const float *ref, const float *qry, int B, int N, int S_local, int s_offset, float *local_out,
+                                   void *const *peer_out, int n_peers, void *workspace, size_t workspace_bytes,
+                                   b200pc_stream_t stream) {
+    B200PC_REQUIRE(B >= 0 && N >= 1 && S_local >= 0 && s_offset >= 0, "rebuild_pack: bad sizes");
+    B200PC_REQUIRE(n_peers >= 0 && n_peers <= MAX_PEERS, "rebuild_pack: at most %d peer buffers", MAX_PEERS);
+    if (B == 0 || S_local == 0) return B200PC_OK;
+    B200PC_REQUIRE(ref && qry && (local_out || n_peers > 0), "rebuild_pack: null pointer");
+    B200PC_REQUIRE(n_peers == 0 || peer_out, "rebuild_pack: n_peers=%d but no pointer array", n_peers);
+    if (!workspace || workspace_bytes < b200pc_rebuild_pack_workspace_bytes(B, N, S_local)) {
+        set_error("rebuild_pack: workspace too small (%zu < %zu bytes)", workspace_bytes, b200pc_rebuild_pack_workspace_bytes(B, N, S_local));
+        return B200PC_EWORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const size_t search_bytes = align_up(b200pc_search_workspace_bytes(B, N, S_local, 1), 256);
+    int32_t *idx = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + search_bytes);
+    const int rc = run_topk_i32(ref, qry, B, N, S_local, 1, B200PC_FORM_DIRECT, idx, nullptr, workspace, search_bytes, st);
+    if (rc != B200PC_OK) return rc;
+    PeerPtrs pp;
+    for (int p = 0; p < MAX_PEERS; ++p) pp.p[p] = p < n_peers ? static_cast<float4 *>(peer_out[p]) : nullptr;
+    const long total = (long)S_local * B;
+    rebuild_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ref, idx, B, N, S_local, s_offset,
+                                                                         reinterpret_cast<float4 *>(local_out), pp, n_peers);
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
+}
 
 extern "C" int b200pc_fusion_group(const float *qry, const float *ref, const float *feat, int B, int N, int S, int k, int Cf,
                                    float *resi, float *nn, float *gfeat, int64_t *idx, void *workspace, size_t workspace_bytes,

@@ -208,6 +208,7 @@ struct SearchArgs {
     int lane_filter;       // 1: refs in registers, queries broadcast (default); 0: queries in registers, refs broadcast
     int n_split, tiles_per_split;
     int64_t *idx_out;      // [B][S][k]   (n_split == 1)
+    int32_t *idx32_out;    // same rows as 32-bit indices (host-buffer callers: halves the read-back); either may be null
     float *dist_out;       // [B][S][k] or null
     float *part_d;         // [B][S][n_split][k]  (top-k partial lists)
     int *part_i;           // [B][S][n_split][k]
@@ -590,17 +591,23 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         const size_t row = (size_t)b * P.S + qi;
         if (P.n_split == 1) {
             int64_t *io = P.idx_out ? P.idx_out + row * k : nullptr;
+            int32_t *io32 = P.idx32_out ? P.idx32_out + row * k : nullptr;
             if (MODE == MODE_TOPK) {
                 float *dout = P.dist_out ? P.dist_out + row * k : nullptr;
                 for (int e = 0; e < k; ++e) {
                     const unsigned long long key = heap_all[e * QPB + slot];
                     if (io) io[e] = (int64_t)(int32_t)(uint32_t)key;     // unfilled slot (a NaN query ranks nothing): -1, distance +inf
+                    if (io32) io32[e] = (int32_t)(uint32_t)key;
                     if (dout) dout[e] = key_to_float((uint32_t)(key >> 32));
                 }
             } else {
                 const int *list = list_all + slot;
                 const int first = cnt[j] > 0 ? list[0] : P.N;
-                for (int e = 0; e < k; ++e) io[e] = e < cnt[j] ? list[e * QPB] : first;
+                for (int e = 0; e < k; ++e) {
+                    const int v = e < cnt[j] ? list[e * QPB] : first;
+                    if (io) io[e] = v;
+                    if (io32) io32[e] = v;
+                }
             }
         } else {
             const size_t prow = (row * P.n_split + split) * k;
@@ -623,7 +630,8 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
 // 4. merge of partial lists (only when the ref range was split)
 // ---------------------------------------------------------------------------------------------
 __global__ void merge_topk_kernel(const float *__restrict__ part_d, const int *__restrict__ part_i, int rows,
-                                  int n_split, int k, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+                                  int n_split, int k, int64_t *__restrict__ idx_out, int32_t *__restrict__ idx32_out,
+                                  float *__restrict__ dist_out) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     unsigned short head[MAX_SPLIT];
@@ -645,24 +653,32 @@ __global__ void merge_topk_kernel(const float *__restrict__ part_d, const int *_
         }
         const int h = head[bs];
         if (idx_out) idx_out[(size_t)row * k + o] = pi[bs * k + h];
+        if (idx32_out) idx32_out[(size_t)row * k + o] = pi[bs * k + h];
         if (dist_out) dist_out[(size_t)row * k + o] = best;
         head[bs] = h + 1;
     }
 }
 
 __global__ void merge_ball_kernel(const int *__restrict__ part_i, const int *__restrict__ part_cnt, int rows,
-                                  int n_split, int k, int N, int64_t *__restrict__ idx_out) {
+                                  int n_split, int k, int N, int64_t *__restrict__ idx_out, int32_t *__restrict__ idx32_out) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
-    int64_t *o = idx_out + (size_t)row * k;
-    int n = 0;
+    int64_t *o = idx_out ? idx_out + (size_t)row * k : nullptr;
+    int32_t *o32 = idx32_out ? idx32_out + (size_t)row * k : nullptr;
+    int n = 0, first = N;
     for (int s = 0; s < n_split && n < k; ++s) {
         const int c = part_cnt[(size_t)row * n_split + s];
         const int *pi = part_i + ((size_t)row * n_split + s) * k;
-        for (int e = 0; e < c && n < k; ++e) o[n++] = pi[e];
+        for (int e = 0; e < c && n < k; ++e, ++n) {
+            if (n == 0) first = pi[e];
+            if (o) o[n] = pi[e];
+            if (o32) o32[n] = pi[e];
+        }
     }
-    const int64_t first = n > 0 ? o[0] : (int64_t)N;
-    for (; n < k; ++n) o[n] = first;
+    for (; n < k; ++n) {
+        if (o) o[n] = first;
+        if (o32) o32[n] = first;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -763,12 +779,12 @@ static int launch_shape(const SearchArgs &a, const SearchPlan &pl, int B, cudaSt
 }
 
 static int run_search(const float *ref, const float *qry, int B, int N, int S, int k, int form, int mode, float r2,
-                      int64_t *idx, float *dist, void *ws, size_t ws_bytes, cudaStream_t st) {
+                      int64_t *idx, int32_t *idx32, float *dist, void *ws, size_t ws_bytes, cudaStream_t st) {
     B200PC_REQUIRE(B >= 0 && N >= 1 && S >= 0 && k >= 1, "search: bad sizes B=%d N=%d S=%d k=%d", B, N, S, k);
     if (B == 0 || S == 0) return B200PC_OK;             // empty work: nothing to validate, empty tensors have null pointers
     B200PC_REQUIRE(ref && qry, "search: null input pointer");
-    B200PC_REQUIRE(idx || dist, "search: no output requested");
-    {   // small reference sets: warp-per-query kernel, one launch, no workspace (small_search.cu)
+    B200PC_REQUIRE(idx || idx32 || dist, "search: no output requested");
+    if (!idx32) {   // small reference sets: warp-per-query kernel, one launch, no workspace (small_search.cu)
         const int rc_small = run_small(ref, qry, B, N, S, k, form, mode, r2, idx, dist, st);
         if (rc_small != -100) return rc_small;
     }
@@ -800,7 +816,7 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
     a.debug_nodrain = tn.nodrain;
     a.lane_filter = tn.filter >= 0 ? tn.filter != 0 : 1;                          // 0: A/B measurement only
-    a.idx_out = idx; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
+    a.idx_out = idx; a.idx32_out = idx32; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;
         char *p = w + pl.packed_bytes;
@@ -818,9 +834,9 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     if (pl.n_split > 1) {
         const int rows = B * S;
         if (mode == MODE_TOPK)
-            merge_topk_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a.part_d, a.part_i, rows, pl.n_split, k, idx, dist);
+            merge_topk_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a.part_d, a.part_i, rows, pl.n_split, k, idx, idx32, dist);
         else
-            merge_ball_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a.part_i, a.part_cnt, rows, pl.n_split, k, N, idx);
+            merge_ball_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a.part_i, a.part_cnt, rows, pl.n_split, k, N, idx, idx32);
         B200PC_LAUNCH_CHECK();
     }
     return B200PC_OK;
@@ -830,13 +846,20 @@ int run_topk(const float *ref, const float *qry, int B, int N, int S, int k, int
              void *ws, size_t ws_bytes, cudaStream_t st) {
     B200PC_REQUIRE(form >= 0 && form <= 2, "knn: unknown distance form %d", form);
     B200PC_REQUIRE(k <= N, "knn: k=%d exceeds the number of reference points N=%d", k, N);
-    return run_search(ref, qry, B, N, S, k, form, MODE_TOPK, 0.f, idx, dist, ws, ws_bytes, st);
+    return run_search(ref, qry, B, N, S, k, form, MODE_TOPK, 0.f, idx, nullptr, dist, ws, ws_bytes, st);
+}
+
+int run_topk_i32(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx32, float *dist,
+                 void *ws, size_t ws_bytes, cudaStream_t st) {
+    B200PC_REQUIRE(form >= 0 && form <= 2, "knn: unknown distance form %d", form);
+    B200PC_REQUIRE(k <= N, "knn: k=%d exceeds the number of reference points N=%d", k, N);
+    return run_search(ref, qry, B, N, S, k, form, MODE_TOPK, 0.f, nullptr, idx32, dist, ws, ws_bytes, st);
 }
 
 int run_ball(const float *ref, const float *qry, int B, int N, int S, float r2, int nsample, int64_t *idx,
              void *ws, size_t ws_bytes, cudaStream_t st) {
     B200PC_REQUIRE(idx || B == 0 || S == 0, "ball_query: null output pointer");
-    return run_search(ref, qry, B, N, S, nsample, B200PC_FORM_QRY_NORM_FIRST, MODE_BALL, r2, idx, nullptr, ws,
+    return run_search(ref, qry, B, N, S, nsample, B200PC_FORM_QRY_NORM_FIRST, MODE_BALL, r2, idx, nullptr, nullptr, ws,
                       ws_bytes, st);
 }
 
@@ -859,6 +882,11 @@ extern "C" size_t b200pc_search_workspace_bytes(int B, int N, int S, int k) {
 extern "C" int b200pc_knn(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
                           float *dist, void *workspace, size_t workspace_bytes, b200pc_stream_t stream) {
     return run_topk(ref, qry, B, N, S, k, form, idx, dist, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int b200pc_knn_i32(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx,
+                              float *dist, void *workspace, size_t workspace_bytes, b200pc_stream_t stream) {
+    return run_topk_i32(ref, qry, B, N, S, k, form, idx, dist, workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int b200pc_ball_query(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
