@@ -9,11 +9,12 @@ no CPU fallback (a missing library or a CPU tensor raises).
   b200pc.pytorch3d_shim    knn_points, knn_gather, chamfer_distance
   b200pc.dropin.install()  run the unmodified reference models on these kernels
   b200pc.polypci           PolyPCI's per-point polynomial fit + evaluation as one device kernel
+  b200pc.io                raw .bin sweeps -> fixed-size clouds by farthest point sampling on the device
   b200pc.synth             deterministic HDL-64-shaped synthetic sweeps (tests / bench)
 """
 from . import _lib  # noqa: F401  (no dlopen at import)
 
-__all__ = ["pointnet2_utils", "pytorch3d_shim", "dropin", "ops", "synth", "dist", "hostio", "pointinet", "polypci"]
+__all__ = ["pointnet2_utils", "pytorch3d_shim", "dropin", "ops", "synth", "dist", "hostio", "io", "pointinet", "polypci"]
 __version__ = "0.1.0"
 
 

@@ -315,3 +315,21 @@ def test_fps_oracle_is_unfused_on_the_near_tie_clouds():
         assert a != b
         got = strict.farthest_point_sample(c[None], 2, np.array([0]))[0, 1]
         assert got == a
+
+
+def test_read_bin_shapes(tmp_path):
+    """b200pc.io.read_bin: the reference's np.fromfile(...).reshape(-1, 5 | 4) (Dataset/InterpolationData.py:142,
+    PointINet20230424/data/interpolation_data.py:34)"""
+    from b200pc import io as bio
+    a = np.arange(35, dtype=np.float32); p = tmp_path / "n.bin"; a.tofile(p)
+    assert bio.read_bin(str(p)).shape == (7, 5) and bio.read_bin(str(p), 5).shape == (7, 5)
+    b = np.arange(24, dtype=np.float32); q = tmp_path / "k.bin"; b.tofile(q)
+    assert bio.read_bin(str(q)).shape == (6, 4)
+    with pytest.raises(ValueError):
+        bio.read_bin(str(q), 5)
+    if ref_loader.available():
+        kitti, nusc = ref_loader.demo_bins()
+        if nusc:
+            assert bio.read_bin(nusc[0], 5).shape[1] == 5
+        if kitti:
+            assert bio.read_bin(kitti[0], 4).shape[0] > 100000
