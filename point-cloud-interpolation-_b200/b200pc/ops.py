@@ -503,7 +503,7 @@ def knn_search(ref, qry, k, form, want_dist=False):
     k = int(k)
     if k > ref.shape[1]:   # torch.topk raises RuntimeError("selected index k out of range")
         raise RuntimeError("selected index k out of range (k=%d > %d reference points)" % (k, ref.shape[1]))
-    idx, dist = _O.knn(ref, qry, k, int(form), bool(want_dist))
+    idx, dist = _O.knn(ref.detach(), qry.detach(), k, int(form), bool(want_dist))      # indices / raw distances carry no gradient
     return (idx, dist) if want_dist else idx
 
 
@@ -513,7 +513,7 @@ def knn_search_i32(ref, qry, k, form):
     k = int(k)
     if k > ref.shape[1]:
         raise RuntimeError("selected index k out of range (k=%d > %d reference points)" % (k, ref.shape[1]))
-    return _O.knn_i32(ref, qry, k, int(form))
+    return _O.knn_i32(ref.detach(), qry.detach(), k, int(form))
 
 
 def ball_query(radius, nsample, xyz, new_xyz):
@@ -521,7 +521,7 @@ def ball_query(radius, nsample, xyz, new_xyz):
     xyz = _prep(xyz, "xyz"); new_xyz = _prep(new_xyz, "new_xyz")
     # `sqrdists > radius ** 2`: python double squared, then compared against fp32 values
     r2 = torch.tensor(float(radius) ** 2, dtype=torch.float32).item()
-    return _O.ball_query(xyz, new_xyz, r2, int(nsample))
+    return _O.ball_query(xyz.detach(), new_xyz.detach(), r2, int(nsample))
 
 
 def fps(xyz, npoint, start, want_xyz=False):
@@ -530,8 +530,13 @@ def fps(xyz, npoint, start, want_xyz=False):
     xyz = _prep(xyz, "xyz")
     start = _idx64(start, xyz.device)
     if want_xyz:
+        if torch.is_grad_enabled() and xyz.requires_grad:
+            # index_points(points, fps_idx) is differentiable in the reference (Utils/Layers.py:25-26): the picks are
+            # made on the detached cloud, the coordinates come from the differentiable gather
+            idx = _O.fps(xyz.detach(), int(npoint), start)
+            return idx, gather(xyz, idx)
         return _O.fps_sample(xyz, int(npoint), start)
-    return _O.fps(xyz, int(npoint), start)
+    return _O.fps(xyz.detach(), int(npoint), start)
 
 
 def gather(points, idx):
