@@ -62,6 +62,7 @@ static void load_tuning() {
     t.bulk = env_int("B200PC_BULK", -1);
     t.fps_cluster = env_int("B200PC_FPS_CLUSTER", 0);
     t.drain = env_int("B200PC_DRAIN", -1);
+    t.grid = env_int("B200PC_GRID", 1);
     g_tuning = t;
     g_tuning_loaded = true;
 }

@@ -50,6 +50,7 @@ struct Tuning {
     int bulk;                                // 0: register-path row movers (gather.cu / group.cu) instead of rowmove.cu
     int fps_cluster;
     int drain;                               // search drain variant (A/B)
+    int grid;                                // 0: top-k searches start from tau = +inf; 1: default (warm start when worth it); 2: always
 };
 const Tuning &tuning();
 

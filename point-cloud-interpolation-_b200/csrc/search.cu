@@ -74,7 +74,12 @@ __device__ __forceinline__ int slot_to_ref(int s, int strided, int n_tiles) {
 }
 static_assert(TILE == 512, "slot_to_ref assumes 512-slot tiles");
 
-__global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad, int strided, float4 *__restrict__ packed) {
+struct GridDesc;
+__device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G);
+__device__ __forceinline__ void grid_count(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z);
+
+__global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad, int strided, float4 *__restrict__ packed,
+                                 const GridDesc *__restrict__ grid, unsigned *__restrict__ counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
     if (p >= n_pad / 2) return;
     const int b = blockIdx.y;
@@ -86,6 +91,7 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
         if (i < N) {
             x[h] = r[i * 3 + 0]; y[h] = r[i * 3 + 1]; z[h] = r[i * 3 + 2];
             w[h] = filter_norm(torch_sq_norm(x[h], y[h], z[h]));
+            if (grid) grid_count(grid, counts, b, x[h], y[h], z[h]);
         } else {
             // padding: the filter sees u = +inf or NaN (never a hit); every exact form gives +inf or NaN (never selected)
             x[h] = CUDART_INF_F; y[h] = 0.0f; z[h] = 0.0f; w[h] = CUDART_INF_F;
@@ -99,6 +105,208 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
     float4 *o = packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2;
     o[0] = make_float4(x[0], x[1], y[0], y[1]);
     o[1] = make_float4(z[0], z[1], w[0], w[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1b. occupancy grid: a conservative STARTING threshold for the top-k searches
+// ---------------------------------------------------------------------------------------------
+// A streaming k-best that starts from tau = +inf pays k(1 + ln(N/k)) heap inserts per query (127 at C2), more than half of
+// them in the first tile, and in lock-step a warp pays the maximum over its lanes (profiles/r01_notes.md: the drain is
+// 50 % of the kernel).  Nothing forces the search to start blind: any radius that provably holds >= k refs bounds the
+// k-th distance.  The refs are counted into a coarse uniform grid (one atomicAdd per ref inside pack_refs_kernel, <= 128
+// cells along the longest axis of their bounding box); a query looks at the counts of the cell box of half-width rho = 0,
+// 1, 2, 3 around its own cell and takes the first box holding >= k refs: every ref of that box is closer than the box's
+// farthest corner, so   tau0 = |q - farthest corner|^2 (1 + 1e-5) + 16 eps (|q|^2 + max|r|^2)
+// is an upper bound of the k-th smallest distance IN THE REFERENCE'S ROUNDING (the second term covers the rounding error
+// of the expanded forms, <= 10.02 eps (|q|^2 + |r|^2)).  Every (query, ref) pair still goes through the
+// filter -- this is brute force with a warm start, and since tau0 is only ever an upper bound the results are
+// bit-identical; at C2 it cuts the inserts per query from 127 to ~45.  Queries with non-finite coordinates, clouds with
+// fewer than k finite refs and boxes that stay short of k refs start from +inf (or the whole bounding box) like before.
+constexpr int GRID_AXIS = 128;             // cells along the longest axis (level 0)
+constexpr int GRID_MAX_CELLS = 131072;     // level-0 cells per batch item
+constexpr int GRID_LEVELS = 5;             // level l has cells of size h * 2^l (a count pyramid)
+constexpr int GRID_STRIDE = 176128;        // counters per batch item: 131072 + 32768 + 8192 + 2048 + 512 rounded up (688 KB)
+constexpr long GRID_MIN_PAIRS = 1L << 24;  // searches smaller than this start blind (the grid would cost more than it saves)
+
+struct GridDesc {            // one per batch item, written by grid_bbox_kernel
+    float lo[3], hi[3];      // bounding box of the finite refs
+    float h, inv_h;          // level-0 cell size (isotropic) and its reciprocal (0 when all refs coincide)
+    int dim[GRID_LEVELS][3]; // cells per axis of every level
+    int off[GRID_LEVELS];    // first counter of every level
+    int n_finite;            // refs with finite coordinates
+    float max_w;             // upper bound of |r|^2 over the finite refs
+    int pad[2];
+};
+static_assert(sizeof(GridDesc) == 128, "GridDesc is 128 bytes");
+
+__device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G) {
+    const float f = (v - lo) * inv_h;
+    int c = f > 0.0f ? (int)fminf(f, 1.0e6f) : 0;      // NaN -> 0
+    return c < G ? c : G - 1;
+}
+
+__global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict__ ref, int N, GridDesc *__restrict__ desc) {
+    const int b = blockIdx.x;
+    const float *r = ref + (size_t)b * N * 3;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    int nf = 0;
+    for (int i0 = threadIdx.x; i0 < N; i0 += 4 * blockDim.x) {          // four points per thread in flight
+        float x[4], y[4], z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const bool in = i < N;
+            x[u] = in ? r[i * 3] : CUDART_NAN_F; y[u] = in ? r[i * 3 + 1] : 0.f; z[u] = in ? r[i * 3 + 2] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (isfinite(x[u]) && isfinite(y[u]) && isfinite(z[u])) {
+                lo[0] = fminf(lo[0], x[u]); hi[0] = fmaxf(hi[0], x[u]);
+                lo[1] = fminf(lo[1], y[u]); hi[1] = fmaxf(hi[1], y[u]);
+                lo[2] = fminf(lo[2], z[u]); hi[2] = fmaxf(hi[2], z[u]);
+                ++nf;
+            }
+    }
+    __shared__ float slo[3][32], shi[3][32];
+    __shared__ int snf[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    nf = __reduce_add_sync(0xffffffffu, nf);
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { slo[a][warp] = lo[a]; shi[a][warp] = hi[a]; }
+        snf[warp] = nf;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        GridDesc d;
+        d.n_finite = 0;
+        for (int a = 0; a < 3; ++a) { d.lo[a] = CUDART_INF_F; d.hi[a] = -CUDART_INF_F; }
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            for (int a = 0; a < 3; ++a) { d.lo[a] = fminf(d.lo[a], slo[a][w]); d.hi[a] = fmaxf(d.hi[a], shi[a][w]); }
+            d.n_finite += snf[w];
+        }
+        float ext[3], emax = 0.0f;
+        d.max_w = 0.0f;
+        for (int a = 0; a < 3; ++a) {
+            ext[a] = d.n_finite > 0 ? d.hi[a] - d.lo[a] : 0.0f;
+            emax = fmaxf(emax, ext[a]);
+            const float m = fmaxf(fabsf(d.lo[a]), fabsf(d.hi[a]));
+            d.max_w += d.n_finite > 0 ? m * m * 1.000001f : 0.0f;
+        }
+        d.dim[0][0] = d.dim[0][1] = d.dim[0][2] = 1;
+        d.h = 0.0f; d.inv_h = 0.0f;
+        if (emax > 0.0f && isfinite(emax)) {
+            float h = emax / (float)GRID_AXIS;
+            for (int it = 0; it < 32; ++it) {
+                long cells = 1;
+                for (int a = 0; a < 3; ++a) {
+                    int g = (int)ceilf(ext[a] / h);
+                    g = g < 1 ? 1 : (g > GRID_AXIS ? GRID_AXIS : g);
+                    d.dim[0][a] = g;
+                    cells *= g;
+                }
+                if (cells <= GRID_MAX_CELLS) break;
+                h *= 2.0f;
+            }
+            d.h = h; d.inv_h = 1.0f / h;
+        }
+        int off = 0;
+        for (int l = 0; l < GRID_LEVELS; ++l) {
+            if (l > 0)
+                for (int a = 0; a < 3; ++a) d.dim[l][a] = (d.dim[l - 1][a] + 1) >> 1;
+            d.off[l] = off;
+            off += d.dim[l][0] * d.dim[l][1] * d.dim[l][2];
+        }
+        d.pad[0] = d.pad[1] = 0;
+        desc[b] = d;
+    }
+}
+
+__device__ __forceinline__ void grid_count(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z) {
+    if (!(isfinite(x) && isfinite(y) && isfinite(z))) return;
+    const GridDesc &g = desc[b];
+    const int cx = grid_cell(x, g.lo[0], g.inv_h, g.dim[0][0]), cy = grid_cell(y, g.lo[1], g.inv_h, g.dim[0][1]),
+              cz = grid_cell(z, g.lo[2], g.inv_h, g.dim[0][2]);
+    atomicAdd(counts + (size_t)b * GRID_STRIDE + ((size_t)cz * g.dim[0][1] + cy) * g.dim[0][0] + cx, 1u);
+}
+
+// the coarser levels: every occupied level-0 cell adds its count to its ancestors (a few thousand atomics per cloud)
+__global__ void __launch_bounds__(256) grid_pyramid_kernel(const GridDesc *__restrict__ desc, unsigned *__restrict__ counts) {
+    const int b = blockIdx.y;
+    const GridDesc &g = desc[b];
+    const int cells = g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    unsigned *base = counts + (size_t)b * GRID_STRIDE;
+    const unsigned n = base[c];
+    if (n == 0) return;
+    const int cx = c % g.dim[0][0], cy = (c / g.dim[0][0]) % g.dim[0][1], cz = c / (g.dim[0][0] * g.dim[0][1]);
+#pragma unroll
+    for (int l = 1; l < GRID_LEVELS; ++l)
+        atomicAdd(base + g.off[l] + (((cz >> l) * g.dim[l][1] + (cy >> l)) * g.dim[l][0] + (cx >> l)), n);
+}
+
+// refs counted in the 3 x 3 x 3 box of level-l cells around (cx, cy, cz): 27 independent loads
+__device__ __forceinline__ unsigned grid_box27(const GridDesc &g, const unsigned *__restrict__ base, int l, int cx, int cy, int cz) {
+    const unsigned *lv = base + g.off[l];
+    const int gx = g.dim[l][0], gy = g.dim[l][1], gz = g.dim[l][2];
+    unsigned v[27];
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                const bool in = (unsigned)x < (unsigned)gx && (unsigned)y < (unsigned)gy && (unsigned)z < (unsigned)gz;
+                v[(dz + 1) * 9 + (dy + 1) * 3 + dx + 1] = in ? __ldg(lv + ((size_t)z * gy + y) * gx + x) : 0u;
+            }
+    unsigned n = 0;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) n += v[i];
+    return n;
+}
+
+// Upper bound of the k-th smallest reference-arithmetic distance from q to the cloud, or +inf (see the section header).
+// Tries the query's own level-0 cell, then the 3^3 box around it at levels 0, 1, 2, 3, 4, then the whole bounding box.
+__device__ __noinline__ float grid_tau0(const GridDesc &g, const unsigned *__restrict__ base, float qx, float qy, float qz, int k, float nq) {
+    if (!(isfinite(qx) && isfinite(qy) && isfinite(qz)) || g.n_finite < k) return CUDART_INF_F;
+    const float q[3] = {qx, qy, qz};
+    int c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[a] = grid_cell(q[a], g.lo[a], g.inv_h, g.dim[0][a]);
+    int lev = -1, rho = 0;
+    if (__ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]) >= (unsigned)k) lev = 0;
+    else {
+        rho = 1;
+        for (int l = 0; l < GRID_LEVELS; ++l)
+            if (grid_box27(g, base, l, c[0] >> l, c[1] >> l, c[2] >> l) >= (unsigned)k) { lev = l; break; }
+    }
+    float bound = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float L = g.lo[a], H = g.hi[a];                      // not found nearby: the whole bounding box holds n_finite >= k refs
+        if (lev >= 0) {
+            const int cl = c[a] >> lev, gl = g.dim[lev][a];
+            const int c0 = cl - rho < 0 ? 0 : cl - rho, c1 = cl + rho >= gl ? gl - 1 : cl + rho;
+            const float hl = g.h * (float)(1 << lev);
+            L = g.lo[a] + (float)c0 * hl;
+            const float Hn = g.lo[a] + (float)(c1 + 1) * hl;  // the last cell also takes the refs clamped into it
+            H = c1 == gl - 1 ? fmaxf(Hn, g.hi[a]) : Hn;
+        }
+        // a ref counted in cell c lies in [lo + c h, lo + (c+1) h] up to the rounding of (v - lo) * inv_h: widen by delta
+        const float delta = 1e-3f * g.h + 1e-6f * fmaxf(fabsf(g.lo[a]), fabsf(g.hi[a]));
+        const float m = fmaxf(fabsf(q[a] - (L - delta)), fabsf((H + delta) - q[a]));
+        bound += m * m;
+    }
+    return bound * 1.00001f + (9.6e-7f * (nq + g.max_w) + 1e-37f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -207,6 +415,8 @@ struct SearchArgs {
     int debug_nodrain;     // measurement only: start with tau = -inf so nothing ever hits
     int lane_filter;       // 1: refs in registers, queries broadcast (default); 0: queries in registers, refs broadcast
     int n_split, tiles_per_split;
+    const GridDesc *grid;  // occupancy grid of the refs (one descriptor per batch item) or null: start from tau = +inf
+    const unsigned *counts;
     int64_t *idx_out;      // [B][S][k]   (n_split == 1)
     int32_t *idx32_out;    // same rows as 32-bit indices (host-buffer callers: halves the read-back); either may be null
     float *dist_out;       // [B][S][k] or null
@@ -352,6 +562,8 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         cnt[j] = 0;
         if (MODE == MODE_TOPK) {
             tau[j] = P.debug_nodrain ? -CUDART_INF_F : CUDART_INF_F;
+            if (P.grid && !P.debug_nodrain && qi < P.S)       // warm start: a radius that provably holds >= k refs
+                tau[j] = grid_tau0(P.grid[b], P.counts + (size_t)b * GRID_STRIDE, x, y, z, k, torch_sq_norm(x, y, z));
             for (int e = 0; e < k; ++e) heap_all[e * QPB + j * NCT + ct] = HEAP_SENTINEL;
             heap_all[k * QPB + j * NCT + ct] = 0ull;   // pad: the smallest key, never selected as a child
         } else {
@@ -360,6 +572,13 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         qrec[j * NCT + ct] = make_float4(-2.0f * x, -2.0f * y, -2.0f * z, filter_threshold(tau[j], torch_sq_norm(x, y, z)));
     }
 
+    bool warp_cold = true;
+    if (MODE == MODE_TOPK) {
+        bool cold = false;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) cold = cold || tau[j] == CUDART_INF_F;
+        warp_cold = __any_sync(FULL, cold);
+    }
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % STAGES;
         mbar_wait(bar_base + 8 * s, (t / STAGES) & 1);
@@ -458,7 +677,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                     const uint32_t hb = smem_u32(heap_all + slot), SB = (uint32_t)QPB * 8u;
                     unsigned short *cand = cand_all + slot;
                     const f32x2 b0 = splat2(qv.x), b1 = splat2(qv.y), b2 = splat2(qv.z);
-                    const float thr = qv.w;
+                    float thr = qv.w;
                     while (__any_sync(FULL, (m0 | m1) != 0u)) {
                         // phase 1: every lane revisits its r-th hit chunk; the refs that pass the filter test on their
                         // own are only recorded, as ONE entry (chunk << 8 | 8-bit mask), at most CAND_CAP per pass.
@@ -504,11 +723,13 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                                     const uint32_t ri = (uint32_t)slot_to_ref(tile_ref0 + off, P.strided, P.n_pad / TILE);
                                     if (d < tau[j] || ri < (uint32_t)lds_u64(hb)) {
                                         heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | ri);
-                                        tau[j] = key_to_float((uint32_t)(lds_u64(hb) >> 32));
+                                        // never above the starting bound: the root is still the +inf sentinel until k refs are in
+                                        tau[j] = fminf(tau[j], key_to_float((uint32_t)(lds_u64(hb) >> 32)));
                                     }
                                 }
                             }
                         }
+                        thr = filter_threshold(tau[j], nq);   // the next pass of this drain filters with the tightened threshold
                     }
                     // publish the tightened threshold to the filters
                     reinterpret_cast<float *>(qrec + slot)[3] = filter_threshold(tau[j], nq);
@@ -542,7 +763,8 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         // that tau tightens quickly, then the lane filter on the second half.  Every other tile: the lane filter on
         // both halves (two 32-bit hit masks per query) and ONE drain.
         uint32_t mask[Q][2];
-        const bool warm = MODE == MODE_TOPK && t == 0;
+        // the warm-up schedule of the first tile is only needed by warps that hold a query starting from tau = +inf
+        const bool warm = MODE == MODE_TOPK && t == 0 && warp_cold;
         int c = 0;
         while (c < CHUNKS_PER_TILE) {
             int nch = CHUNKS_PER_TILE - c;
@@ -693,6 +915,14 @@ static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 // number of waves of resident CTAs: CTA count = B * ceil(S / q_per_block) * n_split against
 // slots = SMs * CTAs-per-SM.  Among the candidates the one with the best wave efficiency wins;
 // ties go to more resident warps.
+// warm start only where it pays: the grid costs a memset, a bounding-box kernel and one atomic per ref
+static bool use_grid(int B, int N, int S) {
+    const int g = tuning().grid;
+    if (g <= 0) return false;
+    if (g >= 2) return true;
+    return N >= 2048 && (long)B * N * S >= GRID_MIN_PAIRS;
+}
+
 bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     const int sms = sm_count();
     const size_t qb = query_bytes(k, mode);
@@ -758,7 +988,11 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
         const size_t rows = (size_t)B * S * pl->n_split;
         pl->part_bytes = align_up(rows * k * 4, 256) * (mode == MODE_TOPK ? 2 : 1) + align_up(rows * 4, 256);
     }
-    pl->total_bytes = pl->packed_bytes + pl->part_bytes;
+    // occupancy grid for the warm start of a top-k search (section 1b): one descriptor + GRID_MAX_CELLS counters per batch item
+    pl->grid_bytes = 0;
+    if (mode == MODE_TOPK && use_grid(B, N, S))
+        pl->grid_bytes = align_up((size_t)B * sizeof(GridDesc), 256) + (size_t)B * GRID_STRIDE * sizeof(unsigned);
+    pl->total_bytes = pl->packed_bytes + pl->part_bytes + pl->grid_bytes;
     return true;
 }
 
@@ -806,9 +1040,23 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     // (every prefix is a well-spread sample; measured 0.32 ms natural vs 0.36 ms strided on C3).
     const Tuning &tn = tuning();
     const int strided = mode == MODE_TOPK && (tn.natural_order >= 0 ? tn.natural_order == 0 : form != B200PC_FORM_QRY_NORM_FIRST);
+    GridDesc *gdesc = nullptr;
+    unsigned *gcounts = nullptr;
+    if (pl.grid_bytes) {
+        char *g = w + pl.packed_bytes + pl.part_bytes;
+        gdesc = reinterpret_cast<GridDesc *>(g);
+        gcounts = reinterpret_cast<unsigned *>(g + align_up((size_t)B * sizeof(GridDesc), 256));
+        B200PC_CUDA(cudaMemsetAsync(gcounts, 0, (size_t)B * GRID_STRIDE * sizeof(unsigned), st));
+        grid_bbox_kernel<<<B, 1024, 0, st>>>(ref, N, gdesc);
+        B200PC_LAUNCH_CHECK();
+    }
     {
         dim3 grid((pl.n_pad / 2 + 255) / 256, B);
-        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, strided, packed);
+        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, strided, packed, gdesc, gcounts);
+        B200PC_LAUNCH_CHECK();
+    }
+    if (gdesc) {
+        grid_pyramid_kernel<<<dim3(GRID_MAX_CELLS / 256, B), 256, 0, st>>>(gdesc, gcounts);
         B200PC_LAUNCH_CHECK();
     }
     SearchArgs a;
@@ -816,6 +1064,7 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
     a.debug_nodrain = tn.nodrain;
     a.lane_filter = tn.filter >= 0 ? tn.filter != 0 : 1;                          // 0: A/B measurement only
+    a.grid = gdesc; a.counts = gcounts;
     a.idx_out = idx; a.idx32_out = idx32; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;
