@@ -138,6 +138,7 @@ struct GridDesc {            // one per batch item, written by grid_bbox_kernel
     int pad[2];
 };
 static_assert(sizeof(GridDesc) == 128, "GridDesc is 128 bytes");
+static_assert(GRID_STRIDE % 4096 == 0, "counters are zeroed 16 bytes at a time");
 
 __device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G) {
     const float f = (v - lo) * inv_h;
@@ -145,9 +146,11 @@ __device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G) 
     return c < G ? c : G - 1;
 }
 
-__global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict__ ref, int N, GridDesc *__restrict__ desc) {
+__global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict__ ref, int N, GridDesc *__restrict__ desc,
+                                                         unsigned *__restrict__ counts) {
     const int b = blockIdx.x;
     const float *r = ref + (size_t)b * N * 3;
+    (void)counts;                                             // zeroed by a memset node before this kernel (a block per cloud is too few to do it here)
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     int nf = 0;
     for (int i0 = threadIdx.x; i0 < N; i0 += 4 * blockDim.x) {          // four points per thread in flight
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict
             d.off[l] = off;
             off += d.dim[l][0] * d.dim[l][1] * d.dim[l][2];
         }
+        if (off > GRID_STRIDE) d.n_finite = 0;               // cannot happen for dims <= 128 and <= 131072 cells; if it did: start blind
         d.pad[0] = d.pad[1] = 0;
         desc[b] = d;
     }
@@ -232,25 +236,28 @@ __global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict
 __device__ __forceinline__ void grid_count(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z) {
     if (!(isfinite(x) && isfinite(y) && isfinite(z))) return;
     const GridDesc &g = desc[b];
+    if (g.n_finite <= 0) return;
     const int cx = grid_cell(x, g.lo[0], g.inv_h, g.dim[0][0]), cy = grid_cell(y, g.lo[1], g.inv_h, g.dim[0][1]),
               cz = grid_cell(z, g.lo[2], g.inv_h, g.dim[0][2]);
     atomicAdd(counts + (size_t)b * GRID_STRIDE + ((size_t)cz * g.dim[0][1] + cy) * g.dim[0][0] + cx, 1u);
 }
 
-// the coarser levels: every occupied level-0 cell adds its count to its ancestors (a few thousand atomics per cloud)
+// the coarser levels: every occupied level-0 cell adds its count to its ancestors (a few thousand atomics per cloud;
+// counting all five levels per ref inside pack_refs_kernel instead tripled that kernel's time: the coarse cells contend)
 __global__ void __launch_bounds__(256) grid_pyramid_kernel(const GridDesc *__restrict__ desc, unsigned *__restrict__ counts) {
     const int b = blockIdx.y;
     const GridDesc &g = desc[b];
+    if (g.n_finite <= 0) return;
     const int cells = g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cells) return;
     unsigned *base = counts + (size_t)b * GRID_STRIDE;
-    const unsigned n = base[c];
-    if (n == 0) return;
-    const int cx = c % g.dim[0][0], cy = (c / g.dim[0][0]) % g.dim[0][1], cz = c / (g.dim[0][0] * g.dim[0][1]);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
+        const unsigned n = base[c];
+        if (n == 0) continue;
+        const int cx = c % g.dim[0][0], cy = (c / g.dim[0][0]) % g.dim[0][1], cz = c / (g.dim[0][0] * g.dim[0][1]);
 #pragma unroll
-    for (int l = 1; l < GRID_LEVELS; ++l)
-        atomicAdd(base + g.off[l] + (((cz >> l) * g.dim[l][1] + (cy >> l)) * g.dim[l][0] + (cx >> l)), n);
+        for (int l = 1; l < GRID_LEVELS; ++l)
+            atomicAdd(base + g.off[l] + (((cz >> l) * g.dim[l][1] + (cy >> l)) * g.dim[l][0] + (cx >> l)), n);
+    }
 }
 
 // refs counted in the 3 x 3 x 3 box of level-l cells around (cx, cy, cz): 27 independent loads
@@ -282,12 +289,17 @@ __device__ __noinline__ float grid_tau0(const GridDesc &g, const unsigned *__res
     int c[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) c[a] = grid_cell(q[a], g.lo[a], g.inv_h, g.dim[0][a]);
-    int lev = -1, rho = 0;
-    if (__ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]) >= (unsigned)k) lev = 0;
-    else {
-        rho = 1;
-        for (int l = 0; l < GRID_LEVELS; ++l)
-            if (grid_box27(g, base, l, c[0] >> l, c[1] >> l, c[2] >> l) >= (unsigned)k) { lev = l; break; }
+    int lev = -1, rho = 1;
+    {   // one round trip for most queries: own cell, level-0 box and level-1 box are requested together
+        const unsigned own = __ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]);
+        const unsigned n0 = grid_box27(g, base, 0, c[0], c[1], c[2]);
+        const unsigned n1 = grid_box27(g, base, 1, c[0] >> 1, c[1] >> 1, c[2] >> 1);
+        if (own >= (unsigned)k) { lev = 0; rho = 0; }
+        else if (n0 >= (unsigned)k) lev = 0;
+        else if (n1 >= (unsigned)k) lev = 1;
+        else
+            for (int l = 2; l < GRID_LEVELS; ++l)
+                if (grid_box27(g, base, l, c[0] >> l, c[1] >> l, c[2] >> l) >= (unsigned)k) { lev = l; break; }
     }
     float bound = 0.0f;
 #pragma unroll
@@ -562,7 +574,9 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         cnt[j] = 0;
         if (MODE == MODE_TOPK) {
             tau[j] = P.debug_nodrain ? -CUDART_INF_F : CUDART_INF_F;
-            if (P.grid && !P.debug_nodrain && qi < P.S)       // warm start: a radius that provably holds >= k refs
+            // warm start: a radius that provably holds >= k refs.  (Computed here rather than by a kernel of its own: that
+            // kernel took 16 us and this prologue got no shorter -- measured, profiles/r02_notes.md.)
+            if (P.grid && !P.debug_nodrain && qi < P.S)
                 tau[j] = grid_tau0(P.grid[b], P.counts + (size_t)b * GRID_STRIDE, x, y, z, k, torch_sq_norm(x, y, z));
             for (int e = 0; e < k; ++e) heap_all[e * QPB + j * NCT + ct] = HEAP_SENTINEL;
             heap_all[k * QPB + j * NCT + ct] = 0ull;   // pad: the smallest key, never selected as a child
@@ -916,11 +930,12 @@ static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 // slots = SMs * CTAs-per-SM.  Among the candidates the one with the best wave efficiency wins;
 // ties go to more resident warps.
 // warm start only where it pays: the grid costs a memset, a bounding-box kernel and one atomic per ref
-static bool use_grid(int B, int N, int S) {
+static bool use_grid(int B, int N, int S, int k) {
     const int g = tuning().grid;
     if (g <= 0) return false;
     if (g >= 2) return true;
-    return N >= 2048 && (long)B * N * S >= GRID_MIN_PAIRS;
+    // measured (tools/grid_probe.py): +6..16 % for k >= 3; a nearest-neighbour search (k = 1) inserts too little to pay for it
+    return k >= 3 && N >= 2048 && (long)B * N * S >= GRID_MIN_PAIRS;
 }
 
 bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
@@ -990,7 +1005,7 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
     }
     // occupancy grid for the warm start of a top-k search (section 1b): one descriptor + GRID_MAX_CELLS counters per batch item
     pl->grid_bytes = 0;
-    if (mode == MODE_TOPK && use_grid(B, N, S))
+    if (mode == MODE_TOPK && use_grid(B, N, S, k))
         pl->grid_bytes = align_up((size_t)B * sizeof(GridDesc), 256) + (size_t)B * GRID_STRIDE * sizeof(unsigned);
     pl->total_bytes = pl->packed_bytes + pl->part_bytes + pl->grid_bytes;
     return true;
@@ -1047,7 +1062,7 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
         gdesc = reinterpret_cast<GridDesc *>(g);
         gcounts = reinterpret_cast<unsigned *>(g + align_up((size_t)B * sizeof(GridDesc), 256));
         B200PC_CUDA(cudaMemsetAsync(gcounts, 0, (size_t)B * GRID_STRIDE * sizeof(unsigned), st));
-        grid_bbox_kernel<<<B, 1024, 0, st>>>(ref, N, gdesc);
+        grid_bbox_kernel<<<B, 1024, 0, st>>>(ref, N, gdesc, gcounts);
         B200PC_LAUNCH_CHECK();
     }
     {
@@ -1056,9 +1071,10 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
         B200PC_LAUNCH_CHECK();
     }
     if (gdesc) {
-        grid_pyramid_kernel<<<dim3(GRID_MAX_CELLS / 256, B), 256, 0, st>>>(gdesc, gcounts);
+        grid_pyramid_kernel<<<dim3(128, B), 256, 0, st>>>(gdesc, gcounts);
         B200PC_LAUNCH_CHECK();
     }
+
     SearchArgs a;
     a.packed = packed; a.strided = strided; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
