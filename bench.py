@@ -689,17 +689,18 @@ def main():
         fma_tf, fma_ms = None, None
     peak = fma_tf if fma_tf else FP32_NOMINAL_TFLOPS
     roofline = {"bound": "fp32_cuda_core", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, one `ncu --set full` capture of this
-                # workload (profiles/r01_ncu_knn.txt): the packed refs are read once, results stay in L2
-                "traffic": 3706112,
+                # dram__bytes_read.sum + dram__bytes_write.sum of search_kernel from one `ncu --set full` capture of this very
+                # call (profiles/r02_ncu_knn.txt: 5.26 MB read = the packed refs and the grid counters once, 0 written: the 16.8 MB
+                # of indices stay in L2 until evicted); a counter, so a constant from the committed capture, not measured live
+                "traffic": 5255680, "traffic_source": "profiles/r02_ncu_knn.txt (ncu --set full, same shape)",
                 "peak_source": "b200pc_fma_peak FFMA2 micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)"
                 if fma_tf else "nominal",
                 "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": achieved / FP32_NOMINAL_TFLOPS,
                 "algorithmic": "8 FLOP per (query, ref) pair x %d pairs per launch" % pairs,
                 "note": "K=3 contraction on FP32 CUDA cores (tensor cores would break the rounding parity); the "
                         "contract's enum is hbm|tensor, this kernel is neither: ncu shows it bound by instruction issue (lane "
-                        "filter 35 %, lock-step heap drain 50 % of 495 M warp instructions, profiles/r01_notes.md), DRAM "
-                        "traffic is 3.7 MB against 17.2 GFLOP"}
+                        "filter 40 %, lock-step heap drain 45 % of 428 M warp instructions, profiles/r02_notes.md), DRAM "
+                        "traffic is 5.3 MB against 17.2 GFLOP"}
 
     # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
     cval, csec, cthreads, ckind = cpu_reference_knn(a, b, reps=3)
@@ -717,8 +718,9 @@ def main():
                     "serial_value": queries_per_step / e2e_res["serial"] / 1e9,
                     "int32_value": queries_per_step / e2e_res["int32"] / 1e9, "int32_d2h_bytes_per_step": d2h_bytes // 2,
                     "numa_cpulist": numa},
-            # pack_refs_kernel + search_kernel per knn_point call (no ref split at C2), timed steps only
-            "gpu_launches": int(args.steps * 2), "abi_calls_incl_warmup": int(abi_calls),
+            # per knn_point call at C2 (no ref split): grid_bbox_kernel, pack_refs_kernel, grid_pyramid_kernel, search_kernel
+            # (+ one memset node for the grid counters); timed steps only
+            "gpu_launches": int(args.steps * 4), "abi_calls_incl_warmup": int(abi_calls),
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     if pn:
         line["pointinet"] = {"metric": "pointinet_interp_frames_per_s", "workload": "C1: PointINet forward, 16384 points, batch 1 per GPU, t=0.5, random weights",
