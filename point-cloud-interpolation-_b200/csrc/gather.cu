@@ -171,8 +171,9 @@ __device__ __forceinline__ float mix3(float a, float wa, float b, float wb, floa
 // and shuffle them; every lane then has 3*ROWS independent 16-byte gathers outstanding.  Row offsets are kept
 // as 32-bit vector indices (the launcher checks B*S*C4 < 2^31) and the register budget is capped so that at
 // least 3 CTAs stay resident: the kernel is a latency chain (idx -> gather -> store), occupancy is what feeds it.
+constexpr int INTERP_MIN_BLOCKS = 4;   // 62 registers, no spills: 32 resident warps instead of 24 (the kernel is a latency chain)
 template <int ROWS>
-__global__ void __launch_bounds__(256, 3) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
+__global__ void __launch_bounds__(256, INTERP_MIN_BLOCKS) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
                                                              const float *__restrict__ w, int S, int C4, long N, long rows_total,
                                                              float4 *__restrict__ out) {
     const int lane = threadIdx.x & 31;

@@ -14,7 +14,7 @@
 namespace b200pc {
 
 int group_bulk(const float *xyz, const float *new_xyz, const float *feat, const int64_t *idx, int B, int N, int S, int K, int D,
-               int xyz_first, float *out, cudaStream_t st);   // rowmove.cu; -100 = shape not served
+               int xyz_first, float *out, int force, cudaStream_t st);   // rowmove.cu; -100 = shape not served
 
 constexpr int GROUP_S = 32;       // centres per block tile of the backward kernel
 
@@ -114,8 +114,8 @@ extern "C" int b200pc_group_points(const float *xyz, const float *new_xyz, const
     const long total = (long)B * K * S;
     B200PC_REQUIRE((total + 255) / 256 < (1L << 31), "group_points: problem too large for one launch");
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (tuning().bulk > 0 && D > 0) {                       // opt-in (B200PC_BULK=1): the asynchronous-copy path (rowmove.cu)
-        const int rc = group_bulk(xyz, new_xyz, feat, idx, B, N, S, K, D, xyz_first != 0, out, as_stream(stream));
+    if (tuning().bulk != 0 && D > 0) {                      // the asynchronous-copy path (rowmove.cu) where it is the faster one
+        const int rc = group_bulk(xyz, new_xyz, feat, idx, B, N, S, K, D, xyz_first != 0, out, tuning().bulk > 0, as_stream(stream));
         if (rc != -100) return rc;
     }
     if (D > 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0)

@@ -225,10 +225,11 @@ __global__ void __launch_bounds__(IN_WARPS * 32, 1) interp_async_kernel(const ch
 // contiguous bytes.  The unit's index block is read once, coalesced, into shared memory (as 32-bit row numbers b*N + i).
 // xyz rows (12 bytes) are read through the LSU.
 // ---------------------------------------------------------------------------------------------
-constexpr int GR_WARPS = 8;
+constexpr int GR_MAX_WARPS = 16;        // warps per CTA are a launch parameter: as many as shared memory allows (the kernel is bound by
+                                        // one warp's instruction latency, not by a pipe: ncu 12 % warps active, 25 % issue active at 8 warps)
 
 template <int NST>
-__global__ void __launch_bounds__(GR_WARPS * 32, 1) group_async_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+__global__ void __launch_bounds__(GR_MAX_WARPS * 32, 1) group_async_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
                                                                        const char *__restrict__ feat, const int64_t *__restrict__ idx,
                                                                        int N, int S, int K, int D, int xyz_first, int ksplit,
                                                                        int units_total, float *__restrict__ out) {
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(GR_WARPS * 32, 1) group_async_kernel(const flo
     const uint32_t warp_bytes = idx_bytes + NST * tile_bytes;
     const uint32_t ibuf = smem_u32(smem) + (uint32_t)warp * warp_bytes;
     const uint32_t data0 = ibuf + idx_bytes;
-    const int gw = blockIdx.x * GR_WARPS + warp, nw = gridDim.x * GR_WARPS;
+    const int nwarps = (int)(blockDim.x >> 5);
+    const int gw = blockIdx.x * nwarps + warp, nw = gridDim.x * nwarps;
     const int s_tiles = (S + 31) / 32;
     const int C = D + 3, xoff = xyz_first ? 0 : D, foff = xyz_first ? 3 : 0, D4 = D >> 2;
     const size_t cstride = (size_t)K * S;
@@ -358,6 +360,12 @@ static int dispatch_nst(int nst, F &&f) {
 }
 static int round_nst(int nst) { return nst >= 8 ? 8 : nst >= 6 ? 6 : nst >= 4 ? 4 : nst >= 3 ? 3 : 2; }
 
+template <typename F>
+static int dispatch_nst12(int nst, F &&f) {
+    if (nst >= 2) return f(std::integral_constant<int, 2>());
+    return f(std::integral_constant<int, 1>());
+}
+
 // index_points through the asynchronous path.  Returns -100 when the shape does not qualify (caller falls back to gather.cu).
 int gather_bulk(const float *points, const int64_t *idx, int B, int N, int C, long R, float *out, int *oob, cudaStream_t st) {
     const uint32_t row_bytes = (uint32_t)C * 4u;
@@ -415,34 +423,46 @@ int interp_bulk(const float *feat, const int64_t *idx, const float *w, int B, in
     });
 }
 
+// force == 0: only where measured faster than the register path (16 warps fit: D <= 64 -- 90.7 vs 102.7 us at C3, D = 64;
+// with 10 warps at D = 128 it is 210 vs 183 us); force != 0: every shape the kernel can serve (A/B, tests).
 int group_bulk(const float *xyz, const float *new_xyz, const float *feat, const int64_t *idx, int B, int N, int S, int K, int D,
-               int xyz_first, float *out, cudaStream_t st) {
+               int xyz_first, float *out, int force, cudaStream_t st) {
+    if (!force && (long)B * S * K < 32768) return -100;                  // small groupings: one wave of the register kernel is quicker
     if (D < 16 || D % 4 != 0 || D > 1024 || (reinterpret_cast<uintptr_t>(feat) & 15) || K > 256) return -100;
     const int cpr = D / 4;
     if (cpr < 32 && 32 % cpr != 0) return -100;                        // rows shorter than 512 bytes must tile an instruction evenly
     if ((long)B * N >= (1L << 31) || (long)B * ((S + 31) / 32) * K >= (1L << 31)) return -100;     // 32-bit row arithmetic in the kernel
     const int sms = sm_count();
-    const long warps = (long)sms * GR_WARPS;
-    const long base_units = (long)B * ((S + 31) / 32);
-    int ksplit = 1;
-    while (ksplit < K && base_units * ksplit < 6 * warps) ksplit <<= 1;
-    if (ksplit > K) ksplit = K;
-    const int kper = (K + ksplit - 1) / ksplit;
-    const long units = base_units * ksplit;
     const uint32_t row_stride = (uint32_t)D * 4u + (((D >> 2) & 1) ? 32u : 16u);
     const size_t tile = (size_t)32 * row_stride;
+    // Many warps with a shallow ring beat few warps with a deep one here (the warp's own dependent chain idx -> copy -> LDS ->
+    // STG is the limiter): one stage per warp, as many warps as fit; two stages only when 16 warps still fit with them.
+    int ksplit = 1, kper = K, nst = 1, nwarps = 0;
+    long units = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const long base_units = (long)B * ((S + 31) / 32);
+        const long warps_guess = (long)sms * (nwarps > 0 ? nwarps : GR_MAX_WARPS);
+        ksplit = 1;
+        while (ksplit < K && base_units * ksplit < 6 * warps_guess) ksplit <<= 1;
+        if (ksplit > K) ksplit = K;
+        kper = (K + ksplit - 1) / ksplit;
+        units = base_units * ksplit;
+        const size_t idx_bytes = ((size_t)32 * (kper | 1) * 4 + 127) & ~(size_t)127;
+        int w1 = (int)(RM_SMEM_BUDGET / (idx_bytes + tile)), w2 = (int)(RM_SMEM_BUDGET / (idx_bytes + 2 * tile));
+        nst = w2 >= GR_MAX_WARPS ? 2 : 1;
+        nwarps = nst == 2 ? w2 : w1;
+        if (nwarps > GR_MAX_WARPS) nwarps = GR_MAX_WARPS;
+        if (nwarps < 4 || (!force && nwarps < GR_MAX_WARPS)) return -100;
+    }
     const size_t idx_bytes = ((size_t)32 * (kper | 1) * 4 + 127) & ~(size_t)127;
-    const size_t avail = RM_SMEM_BUDGET / GR_WARPS;
-    if (avail < idx_bytes + 2 * tile) return -100;
-    const int nst = round_nst((int)((avail - idx_bytes) / tile));
-    const int grid = (int)((units + GR_WARPS - 1) / GR_WARPS < sms ? (units + GR_WARPS - 1) / GR_WARPS : sms);
-    const size_t smem = (size_t)GR_WARPS * (idx_bytes + nst * tile);
-    return dispatch_nst(nst, [&](auto tag) -> int {
+    const int grid = (int)((units + nwarps - 1) / nwarps < sms ? (units + nwarps - 1) / nwarps : sms);
+    const size_t smem = (size_t)nwarps * (idx_bytes + nst * tile);
+    return dispatch_nst12(nst, [&](auto tag) -> int {
         constexpr int NST = decltype(tag)::value;
         auto kern = group_async_kernel<NST>;
         B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, GR_WARPS * 32, smem, st>>>(xyz, new_xyz, reinterpret_cast<const char *>(feat), idx, N, S, K, D, xyz_first, ksplit,
-                                                (int)units, out);
+        kern<<<grid, nwarps * 32, smem, st>>>(xyz, new_xyz, reinterpret_cast<const char *>(feat), idx, N, S, K, D, xyz_first, ksplit,
+                                              (int)units, out);
         B200PC_LAUNCH_CHECK();
         return B200PC_OK;
     });

@@ -120,6 +120,7 @@ def test_async_row_movers_equal_the_register_path(cuda_dev, monkeypatch):
         pts = torch.randn(B, N, C, generator=g).to(cuda_dev)
         idx = torch.randint(-N, N, (B, R), generator=g).to(cuda_dev)
         idx[0, 0] = N + 3                                              # out of range: a row of zeros on both paths
+        monkeypatch.setenv("B200PC_BULK", "0"); ops.reload_tuning()
         want = P.index_points(pts, idx)
         monkeypatch.setenv("B200PC_BULK", "1"); ops.reload_tuning()
         got = P.index_points(pts, idx)
@@ -132,6 +133,7 @@ def test_async_row_movers_equal_the_register_path(cuda_dev, monkeypatch):
         idx = P.knn_point(K, xyz, new)
         idx[0, 5, 0] = 3000                                            # the ball query's empty-ball sentinel
         for first in (True, False):
+            monkeypatch.setenv("B200PC_BULK", "0"); ops.reload_tuning()
             want = P.group_points(xyz, new, feat, idx, xyz_first=first)
             monkeypatch.setenv("B200PC_BULK", "1"); ops.reload_tuning()
             got = P.group_points(xyz, new, feat, idx, xyz_first=first)
@@ -141,6 +143,7 @@ def test_async_row_movers_equal_the_register_path(cuda_dev, monkeypatch):
     for C in (128, 256, 64):
         sf = torch.randn(2, 600, C, generator=g).to(cuda_dev)
         _, i3, w3 = P.three_nn_weights(xyz, sparse)
+        monkeypatch.setenv("B200PC_BULK", "0"); ops.reload_tuning()
         want = P.three_interpolate(sf, i3, w3)
         monkeypatch.setenv("B200PC_BULK", "1"); ops.reload_tuning()
         got = P.three_interpolate(sf, i3, w3)

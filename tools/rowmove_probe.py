@@ -35,7 +35,7 @@ def ab(name, fn, nbytes):
     res = {}
     outs = {}
     for mode in ("0", "1"):
-        os.environ["B200PC_BULK"] = mode
+        os.environ["B200PC_BULK"] = mode; ops.reload_tuning()
         outs[mode] = fn()
         s = t(fn)
         res[mode] = s
