@@ -431,7 +431,7 @@ def _rebuild_pack(ref, qry, s_offset, peer_ptrs):
 # ---- a9 ----------------------------------------------------------------------------------
 def _chamfer_fake(x, y):
     B, N, M = x.shape[0], x.shape[1], y.shape[1]
-    return _f32(like=x), _f32(B, N, like=x), _i64(B, N, like=x), _f32(B, M, like=x), _i64(B, M, like=x)
+    return _f32((), like=x), _f32(B, N, like=x), _i64(B, N, like=x), _f32(B, M, like=x), _i64(B, M, like=x)
 
 
 @_register("chamfer_fwd", _chamfer_fake)
@@ -440,13 +440,13 @@ def _chamfer_fwd(x, y):
     dev = x.device
     dx = _f32(B, N, like=x); ix = _i64(B, N, like=x)
     dy = _f32(B, M, like=x); iy = _i64(B, M, like=x)
-    loss = _f32(1, like=x)
+    loss = _f32((), like=x)
     lib = _lib.load()
     nws = max(lib.b200pc_search_workspace_bytes(B, M, N, 1), lib.b200pc_search_workspace_bytes(B, N, M, 1))
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_chamfer_fwd, _ptr(x), _ptr(y), B, N, M, _ptr(dx), _ptr(ix), _ptr(dy), _ptr(iy), _ptr(loss), _ptr(ws), nws,
           _stream(dev))
-    return loss.view(()), dx, ix, dy, iy
+    return loss, dx, ix, dy, iy
 
 
 @_register("chamfer_bwd", lambda x, y, ix, iy, gloss: (torch.empty_like(x), torch.empty_like(y)))
