@@ -79,7 +79,8 @@ int b200pc_knn_i32(const float *ref, const float *qry, int B, int N, int S, int 
 
 /* ---- a2: query_ball_point(radius, nsample, xyz, new_xyz)  Utils/Pointnet2Utils.py:88-108 -- */
 /* r2 = (float)(radius*radius) computed in double by the caller.  idx [B,S,nsample] int64:
- * the nsample lowest-index refs with NOT(d > r2), padded with the first; N if the ball is empty. */
+ * the nsample lowest-index refs with d <= r2, padded with the first; N if the ball is empty.  (For finite inputs this is
+ * the reference's NOT(d > r2); a NaN distance -- non-finite coordinates -- is never a hit, on either kernel path.) */
 int b200pc_ball_query(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
                       int64_t *idx, void *workspace, size_t workspace_bytes, b200pc_stream_t stream);
 

@@ -59,18 +59,28 @@ class RngTape:
     def finish_recording(self):
         total = sum(s[2] for s in self.specs)
         self.flat_dev = torch.empty(total, dtype=torch.long, device=self.device)
-        self.flat_host = torch.empty(total, dtype=torch.long).pin_memory()
+        # two pinned staging buffers: frame i+1 is drawn into one while frame i's upload may still be reading the other
+        self.flat_host = [torch.empty(total, dtype=torch.long).pin_memory() for _ in range(2)]
+        self.uploaded = [None, None]          # event recorded after the upload out of each staging buffer
+        self.turn = 0
         off, views = 0, []
         for s, old in zip(self.specs, self.views):
             v = self.flat_dev[off:off + s[2]]; v.copy_(old); views.append(v); off += s[2]
         self.views, self.mode = views, "replay"
 
     def refill(self):
+        """redraw the whole sequence for the next frame on the CPU generator and upload it with one copy"""
+        self.pos = 0
+        buf = self.flat_host[self.turn]
+        if self.uploaded[self.turn] is not None:
+            self.uploaded[self.turn].synchronize()      # the upload that last read this staging buffer has finished
         off = 0
         for s in self.specs:
-            self.flat_host[off:off + s[2]] = self._draw(s); off += s[2]
-        self.flat_dev.copy_(self.flat_host, non_blocking=True)
-        self.pos = 0
+            buf[off:off + s[2]] = self._draw(s); off += s[2]
+        self.flat_dev.copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(self.device))
+        self.uploaded[self.turn] = ev
+        self.turn ^= 1
 
 
 def cuda_backend(tape=None):
@@ -376,7 +386,9 @@ class GraphedPointINet:
         for dst, src in zip(self.static_in[:4], (points1, points2, features1, features2)):
             dst.copy_(src)
         self.tape.mode = "record"
+        rng_state = torch.get_rng_state()                 # capturing must not consume the caller's CPU-RNG stream: the first
         self._forward()                                   # eager warm-up: records the RNG sequence, sizes every workspace
+        torch.set_rng_state(rng_state)                    # replayed frame then makes the draws the reference's first forward would
         self.tape.finish_recording()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))

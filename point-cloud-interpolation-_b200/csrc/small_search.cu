@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_search_kernel(const fl
             for (int i = 0; i < NI && cnt < k; ++i) {
                 const int r = i * 32 + lane;
                 const float d = dist_scalar<FORM>(sx[r], sy[r], sz[r], sn[r], qx, qy, qz, qn);
-                const bool hit = r < N && !(d > r2);
+                const bool hit = r < N && d <= r2;        // same predicate as the streaming kernel: a NaN distance is never a hit
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
                 if (m) {
                     if (cnt == 0) first = i * 32 + (__ffs(m) - 1);

@@ -255,3 +255,21 @@ def test_knn_spatially_sorted_clouds_exact_and_not_pathological(cuda_dev, monkey
     monkeypatch.setenv("B200PC_NATURAL_ORDER", "1")                       # refs visited in index order: same answer
     idx2, dist2 = ops.knn_search(r, q, 16, form, want_dist=True)
     assert torch.equal(idx, idx2) and torch.equal(dist, dist2)
+
+
+@pytest.mark.parametrize("small_path", ["1", "0"])
+def test_ball_query_non_finite_inputs_same_on_both_paths(cuda_dev, monkeypatch, small_path):
+    """a NaN / inf coordinate makes NaN distances: never a hit, whichever kernel path serves the call (the streaming and the
+    warp-per-query kernels use the same predicate d <= r2); rows with finite inputs are unaffected"""
+    if small_path == "0":
+        monkeypatch.setenv("B200PC_SMALL_PATH", "0"); ops.reload_tuning()
+    a, b = synth.batch_pairs(12, 1, 900)
+    ref, qry = a.copy(), b[:, :200].copy()
+    ref[0, 5] = [np.nan, 0.0, 0.0]; ref[0, 17] = [np.inf, 1.0, 2.0]
+    qry[0, 3] = [np.nan, np.nan, np.nan]
+    got = P.query_ball_point(1.5, 16, _t(ref, cuda_dev), _t(qry, cuda_dev)).cpu().numpy()
+    clean = ref.copy(); clean[0, 5] = 1e6; clean[0, 17] = -1e6                   # the same cloud with the bad points moved far away
+    want = strict.query_ball_point(1.5, 16, clean, np.nan_to_num(qry, nan=1e7))
+    assert not np.isin(got, [5, 17]).any()
+    np.testing.assert_array_equal(np.delete(got, 3, axis=1), np.delete(want, 3, axis=1))
+    assert (got[0, 3] == 900).all()                                              # the NaN query: empty ball -> N
