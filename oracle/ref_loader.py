@@ -180,3 +180,24 @@ def rebind_pytorch3d(provider):
         for n in ("knn_points", "knn_gather", "chamfer_distance"):
             if n in mod.__dict__:
                 setattr(mod, n, getattr(provider, n))
+
+
+def polypci_models(pytorch3d_provider=None):
+    """PolyPCI/Models/Models_V1.py (FlowNet3D + PolyPCI: rebuild :102-114, fitting_and_predict :116-124, forward :126-222).
+    The file imports `Dataset.Dataset.NuscenesDataset` (PolyPCI's own loader, open3d-based) and `Utils.*` (byte-identical to
+    the top-level copies): PolyPCI/ goes on sys.path behind the repository root, and a placeholder stands in for the
+    dataset module when the top-level `Dataset` package (which has no Dataset.py) was imported first."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REF_ROOT)
+    install_stubs(pytorch3d_provider)
+    if "Dataset.Dataset" not in sys.modules:
+        try:
+            if REF_ROOT not in sys.path:
+                sys.path.insert(0, REF_ROOT)
+            importlib.import_module("Dataset.Dataset")
+        except Exception:
+            _stub("Dataset"); _stub("Dataset.Dataset", NuscenesDataset=object)
+    poly_root = os.path.join(REF_ROOT, "PolyPCI")
+    if poly_root not in sys.path:
+        sys.path.append(poly_root)
+    return _import_from(REF_ROOT, "Models.Models_V1")

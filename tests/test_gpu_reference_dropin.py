@@ -212,3 +212,32 @@ def test_fork_isapcinet_forward_and_backward(cuda_dev, installed):
     loss.backward()
     g = net.flow.set_conv1.conv[0].weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+
+
+@needs_ref
+def test_polypci_forward(cuda_dev, installed):
+    """PolyPCI/Models/Models_V1.py:92-222 (PolyPCI, field=2): four FlowNet3D passes, `rebuild` = knn_points(K=1, return_nn)
+    (:102-114) after every warp, then the reference's own host-side polynomial fit (:116-124, :191-219 -- left as it is: the
+    forward hard-codes the .cpu() / numpy / .cuda() round trip).  CPU arm = the same module with the reference's primitives;
+    `rebuild` picks nearest neighbours of warped points that differ between the arms by conv rounding, so a few picks may
+    swap: 99 % of the output coordinates within 1e-3."""
+    import contextlib, io
+    poly = ref_loader.polypci_models(ref_loader.strict_provider())
+    torch.manual_seed(6)
+    net = poly.PolyPCI(field=2, degree=2).eval()
+    n = 2048
+    frames = [torch.from_numpy(synth.frame_pair(60 + i, n)[0]).t().unsqueeze(0).contiguous() for i in range(5)]
+    ini = torch.zeros(1, 3, n); t = torch.tensor([0.5]); T = [[0.0, -1.0, 1.0, -2.0, 2.0]]
+    torch.manual_seed(3005)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):      # the reference prints every shape
+        want = net([frames[1], frames[3]], frames[0], [frames[2], frames[4]], t, T, ini)
+    installed(True)
+    net = net.to(cuda_dev)
+    fr = [f.to(cuda_dev) for f in frames]
+    torch.manual_seed(3005)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        got = net([fr[1], fr[3]], fr[0], [fr[2], fr[4]], t.to(cuda_dev), T, ini.to(cuda_dev))
+    assert got.shape == (1, 3, n) and got.is_cuda
+    _close(got, want, rtol=1e-3, atol=1e-3, frac=0.99)
+    # the device-side fit (b200pc.polypci, SURVEY 8f rank 4) on the frames the reference stacked would give the same frame:
+    # checked directly against the reference's fitting_and_predict in tests/test_gpu_ops.py
