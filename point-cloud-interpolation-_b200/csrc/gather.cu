@@ -171,9 +171,11 @@ __device__ __forceinline__ float mix3(float a, float wa, float b, float wb, floa
 // and shuffle them; every lane then has 3*ROWS independent 16-byte gathers outstanding.  Row offsets are kept
 // as 32-bit vector indices (the launcher checks B*S*C4 < 2^31) and the register budget is capped so that at
 // least 3 CTAs stay resident: the kernel is a latency chain (idx -> gather -> store), occupancy is what feeds it.
-constexpr int INTERP_MIN_BLOCKS = 4;   // 62 registers, no spills: 32 resident warps instead of 24 (the kernel is a latency chain)
+// resident CTAs asked of ptxas: 2 rows in flight fit 62 registers without spills = 4 CTAs = 32 warps instead of 24 (the
+// kernel is a latency chain: 59.7 -> 51.3 us at C3); 1 row fits 6 CTAs
+constexpr int interp_min_blocks(int rows) { return rows == 1 ? 6 : rows == 2 ? 4 : 2; }
 template <int ROWS>
-__global__ void __launch_bounds__(256, INTERP_MIN_BLOCKS) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
+__global__ void __launch_bounds__(256, interp_min_blocks(ROWS)) interp_rows_kernel(const float4 *__restrict__ feat, const int64_t *__restrict__ idx,
                                                              const float *__restrict__ w, int S, int C4, long N, long rows_total,
                                                              float4 *__restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -390,7 +392,8 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
         if (tn.interp_flat >= 0 ? tn.interp_flat != 0 : C / 4 < 32) {   // default: flat for narrow rows (C < 128)
             const long total = rows * (C / 4);
             interp_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, total, o4);
-        } else if (rw == 8) interp_rows_kernel<8><<<wave_grid(rows * 32 / 8, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
+        } else if (rw == 1) interp_rows_kernel<1><<<wave_grid(rows * 32, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
+        else if (rw == 8) interp_rows_kernel<8><<<wave_grid(rows * 32 / 8, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
         else if (rw == 2) interp_rows_kernel<2><<<wave_grid(rows * 32 / 2, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
         else interp_rows_kernel<4><<<wave_grid(rows * 32 / 4, 256, 1), 256, 0, st>>>(f4, idx, weight, S, C / 4, (long)N, rows, o4);
     } else {
