@@ -12,10 +12,6 @@
 
 namespace b200pc {
 
-// rowmove.cu: the TMA (cp.async.bulk) row movers; -100 = shape not served
-int gather_bulk(const float *points, const int64_t *idx, int B, int N, int C, long R, float *out, int *oob, cudaStream_t st);
-int interp_bulk(const float *feat, const int64_t *idx, const float *w, int B, int S, int N, int C, float *out, cudaStream_t st);
-
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int wave_grid(long work_items, int threads, int per_thread) {
@@ -313,10 +309,6 @@ extern "C" int b200pc_gather(const float *points, const int64_t *idx, int B, int
     if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
         const long rows = (long)B * R;
         const Tuning &tn = tuning();                        // cached knobs (not part of the ABI)
-        if (tn.bulk > 0) {                                  // opt-in (B200PC_BULK=1): the asynchronous-copy path (rowmove.cu), see its header
-            const int rc = gather_bulk(points, idx, B, N, C, (long)R, out, oob_flag, st);
-            if (rc != -100) return rc;
-        }
         const int rw = tn.gather_rows > 0 ? tn.gather_rows : 8;
         if (tn.gather_flat >= 0 ? tn.gather_flat != 0 : C / 4 < 32) {   // default: flat for narrow rows (a warp per row idles lanes when C < 128)
             const long total = rows * (C / 4);
@@ -382,10 +374,6 @@ extern "C" int b200pc_three_interpolate(const float *feat, const int64_t *idx, c
     if (C % 4 == 0 && aligned16(feat) && aligned16(out) && (long)B * S * (C / 4) < (1L << 31)) {
         const long rows = (long)B * N;
         const Tuning &tn = tuning();                        // cached knobs (not part of the ABI)
-        if (tn.bulk > 0) {                                  // opt-in (B200PC_BULK=1): the asynchronous-copy path (rowmove.cu), see its header
-            const int rc = interp_bulk(feat, idx, weight, B, S, N, C, out, st);
-            if (rc != -100) return rc;
-        }
         const int rw = tn.interp_rows > 0 ? tn.interp_rows : 2;
         const float4 *f4 = reinterpret_cast<const float4 *>(feat);
         float4 *o4 = reinterpret_cast<float4 *>(out);

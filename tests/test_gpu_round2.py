@@ -113,25 +113,17 @@ def test_rebuild_pack_records(cuda_dev):
     assert torch.equal(full[1000:3000].view(torch.int32), rec.view(torch.int32)) and not full[:1000].any() and not full[3000:].any()
 
 
-def test_async_row_movers_equal_the_register_path(cuda_dev, monkeypatch):
-    """rowmove.cu (B200PC_BULK=1) against gather.cu / group.cu: identical bits, ragged sizes, hostile indices"""
+def test_async_group_points_equals_the_register_path(cuda_dev, monkeypatch):
+    """rowmove.cu (forced with B200PC_BULK=1, default for D <= 64) against group.cu (B200PC_BULK=0): identical bits,
+    ragged sizes, both layouts, the ball query's empty-ball sentinel"""
     g = torch.Generator().manual_seed(7)
-    for (B, N, R, C) in [(2, 1000, 333, 128), (1, 5000, 4097, 64), (3, 700, 50, 256), (2, 900, 1, 1024)]:
-        pts = torch.randn(B, N, C, generator=g).to(cuda_dev)
-        idx = torch.randint(-N, N, (B, R), generator=g).to(cuda_dev)
-        idx[0, 0] = N + 3                                              # out of range: a row of zeros on both paths
-        monkeypatch.setenv("B200PC_BULK", "0"); ops.reload_tuning()
-        want = P.index_points(pts, idx)
-        monkeypatch.setenv("B200PC_BULK", "1"); ops.reload_tuning()
-        got = P.index_points(pts, idx)
-        monkeypatch.delenv("B200PC_BULK"); ops.reload_tuning()
-        assert torch.equal(got, want), (B, N, R, C)
     a, b = synth.batch_pairs(36, 2, 3000)
     xyz = _t(a, cuda_dev); new = _t(b[:, :777].copy(), cuda_dev)
-    for D, K in [(64, 16), (128, 5), (32, 9), (16, 3)]:
+    for D, K in [(64, 16), (128, 5), (32, 9), (16, 3), (256, 2)]:
         feat = torch.randn(2, 3000, D, generator=g).to(cuda_dev)
         idx = P.knn_point(K, xyz, new)
         idx[0, 5, 0] = 3000                                            # the ball query's empty-ball sentinel
+        idx[1, 7, K - 1] = -1                                          # wraps to the last point
         for first in (True, False):
             monkeypatch.setenv("B200PC_BULK", "0"); ops.reload_tuning()
             want = P.group_points(xyz, new, feat, idx, xyz_first=first)
@@ -139,16 +131,7 @@ def test_async_row_movers_equal_the_register_path(cuda_dev, monkeypatch):
             got = P.group_points(xyz, new, feat, idx, xyz_first=first)
             monkeypatch.delenv("B200PC_BULK"); ops.reload_tuning()
             assert torch.equal(got, want), (D, K, first)
-    sparse = xyz[:, ::5].contiguous()
-    for C in (128, 256, 64):
-        sf = torch.randn(2, 600, C, generator=g).to(cuda_dev)
-        _, i3, w3 = P.three_nn_weights(xyz, sparse)
-        monkeypatch.setenv("B200PC_BULK", "0"); ops.reload_tuning()
-        want = P.three_interpolate(sf, i3, w3)
-        monkeypatch.setenv("B200PC_BULK", "1"); ops.reload_tuning()
-        got = P.three_interpolate(sf, i3, w3)
-        monkeypatch.delenv("B200PC_BULK"); ops.reload_tuning()
-        assert torch.equal(got, want), C
+            assert torch.equal(P.group_points(xyz, new, feat, idx, xyz_first=first), want)      # whichever the default picks
 
 
 def test_host_pipeline_overlapped_calls(cuda_dev):

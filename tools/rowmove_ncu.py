@@ -1,5 +1,5 @@
-"""driver for ncu captures of the row movers: python tools/rowmove_ncu.py <bulk 0|1> ; one call of index_points,
-three_interpolate and group_points each at the C3 shapes (B=16)."""
+"""driver for ncu captures of the row movers: python tools/rowmove_ncu.py <bulk 0|1> (0 / 1: register / asynchronous
+group_points); one call of index_points, three_interpolate and group_points each at the C3 shapes (B=16)."""
 import os
 import sys
 

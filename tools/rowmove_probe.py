@@ -1,6 +1,6 @@
-"""A/B of the HBM-bound row movers: register path (gather.cu / group.cu, B200PC_BULK=0) vs the TMA path (rowmove.cu,
-B200PC_BULK=1) on the C3 shapes and a few others; checks that both paths return identical bits.  L2 flushed before
-every timed call.  Usage: python tools/rowmove_probe.py [quick]"""
+"""A/B of group_points: register path (group.cu, B200PC_BULK=0) vs the asynchronous-copy path (rowmove.cu, B200PC_BULK=1)
+on the C3 shapes; index_points / three_interpolate are timed too (their asynchronous variants were measured with an earlier
+version of this probe and removed: both columns now show the register kernels).  L2 flushed before every timed call."""
 import json
 import os
 import sys
