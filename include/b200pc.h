@@ -55,6 +55,8 @@ void b200pc_tuning_reload(void);
 /* scratch for any neighbour search (knn / ball_query / three_nn / chamfer) of S queries
  * against N refs per batch item with lists of length k (k = nsample for the ball query). */
 size_t b200pc_search_workspace_bytes(int B, int N, int S, int k);
+/* FPS keeps a cloud in the registers of one thread-block cluster and needs NO scratch: this query returns a token 256 and
+ * b200pc_fps ignores its workspace arguments (both kept so that every compute entry has the same calling shape). */
 size_t b200pc_fps_workspace_bytes(int B, int N);
 
 /* ---- a1: square_distance(src, dst)  Utils/Pointnet2Utils.py:20-41 ---------------------- */
@@ -203,7 +205,10 @@ int b200pc_chamfer_bwd(const float *x, const float *y, const int64_t *ix, const 
 int b200pc_fma_peak(int iters, double *tflops, double *ms, b200pc_stream_t stream);
 
 /* ---- host-buffer convenience wrappers (non-torch callers) -------------------------------- */
-/* Same semantics as above with HOST pointers: allocate, copy in, run, copy out, synchronise. */
+/* Same semantics as above with HOST pointers: allocate, copy in, run, copy out, synchronise -- a convenience for plain C /
+ * numpy callers, deliberately simple (pageable copies, a cudaMalloc per call, nothing overlapped).  Callers that stream
+ * many clouds should hold device buffers and pinned host buffers themselves and overlap the copies of consecutive calls
+ * the way b200pc.hostio.KnnHostPipeline does (two streams; b200pc_knn_i32 halves the read-back). */
 int b200pc_knn_host(const float *ref, const float *qry, int B, int N, int S, int k, int form, int64_t *idx,
                     float *dist);
 int b200pc_ball_query_host(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
