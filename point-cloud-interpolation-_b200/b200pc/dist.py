@@ -79,14 +79,18 @@ class PeerSlab:
         self.hdl.barrier()
 
 
-def rebuild_sharded(refs, queries, mode="nccl", slab=None, group=None):
+def rebuild_sharded(refs, queries, mode="nccl", slab=None, group=None, pack=None):
     """`PolyPCI.rebuild` (PolyPCI/Models/Models_V1.py:102-114) with the queries sharded over the ranks and the refs
     replicated: every rank searches S/world queries and the (index, neighbour) records are assembled on every rank.
       mode "nccl": ONE all_gather_into_tensor of the [S/world, B, 4] record slabs (16 bytes per query);
       mode "peer": the producing kernel stores its slab into every rank's symmetric buffer (`slab`, a PeerSlab),
                    followed by one symmetric-memory barrier -- no collective kernel at all.
-    S must divide evenly (C5: 65 536 / 8).  Returns the assembled records [S,B,4] (ops.unpack_rebuild splits them)."""
-    from . import ops
+    S must divide evenly (C5: 65 536 / 8).  Returns the assembled records [S,B,4] (ops.unpack_rebuild splits them).
+    `pack(refs, query_slice, s_offset, peer_ptrs)` defaults to ops.rebuild_pack (the CUDA entry); the gloo tests on CPU pass
+    a stand-in, this module itself never computes anything."""
+    if pack is None:
+        from . import ops
+        pack = lambda r, q, s_offset, peer_ptrs: ops.rebuild_pack(r, q, s_offset=s_offset, peer_ptrs=peer_ptrs)
     world = dist.get_world_size(group); rank = dist.get_rank(group)
     B, S, _ = queries.shape
     if S % world:
@@ -95,10 +99,10 @@ def rebuild_sharded(refs, queries, mode="nccl", slab=None, group=None):
     mine = queries[:, rank * per:(rank + 1) * per].contiguous()
     if mode == "peer":
         slab.barrier()                                   # every peer is done reading the previous contents
-        ops.rebuild_pack(refs, mine, s_offset=rank * per, peer_ptrs=slab.ptrs)
+        pack(refs, mine, rank * per, slab.ptrs)
         slab.barrier()                                   # every peer's stores have landed
         return slab.buf
-    local = ops.rebuild_pack(refs, mine, s_offset=0, peer_ptrs=())
+    local = pack(refs, mine, 0, ())
     out = torch.empty(S, B, 4, dtype=torch.float32, device=queries.device)
     dist.all_gather_into_tensor(out, local, group=group)
     return out

@@ -37,6 +37,21 @@ def _worker(rank, world, port, q):
     d_full, i_full = ref_torch.knn_points_dense(qry, refs, 4)
     d, i = bdist.query_sharded(lambda s: ref_torch.knn_points_dense(s, refs, 4), qry)
     ok2 = torch.equal(i, i_full) and torch.equal(d, d_full)
+    # C5 rebuild: S/world queries per rank, ONE all_gather_into_tensor of the [S/world, B, 4] record slabs
+    def pack_cpu(r, q, s_offset, peer_ptrs):
+        d, i = ref_torch.knn_points_dense(q, r, 1)                                  # [B,s,1]
+        nn = ref_torch.gather_rows(r, i)[:, :, 0]                                  # [B,s,3]
+        rec = torch.cat([i.to(torch.int32).view(torch.float32), nn], dim=-1)       # {index bits, x, y, z}
+        return rec.transpose(0, 1).contiguous()                                    # s-major like the CUDA entry
+    q700 = qry[:, :700].contiguous()
+    full = pack_cpu(refs, q700, 0, ())
+    got_r = bdist.rebuild_sharded(refs, q700, mode="nccl", pack=pack_cpu)
+    ok1 = ok1 and torch.equal(got_r.view(torch.int32), full.view(torch.int32))
+    try:
+        bdist.rebuild_sharded(refs, qry, mode="nccl", pack=pack_cpu)               # 701 queries do not divide over 2 ranks
+        ok1 = False
+    except ValueError:
+        pass
     mine = bdist.batch_shard([refs, qry])
     ok3 = mine[0].shape[0] == 1 and torch.equal(mine[0][0], refs[rank])
     q.put((rank, ok1, ok2, ok3))
