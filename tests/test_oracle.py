@@ -333,3 +333,31 @@ def test_read_bin_shapes(tmp_path):
             assert bio.read_bin(nusc[0], 5).shape[1] == 5
         if kitti:
             assert bio.read_bin(kitti[0], 4).shape[0] > 100000
+
+
+def test_knn_points_and_chamfer_against_an_independent_kd_tree():
+    """a8 / a9 are "parity unpinned" (pytorch3d is neither vendored nor pinned by the reference).  Beside the dense float64
+    formula, an INDEPENDENT implementation of the same semantics: scipy's cKDTree in float64.  On every query whose k+1
+    nearest float64 distances are separated by more than fp32 rounding the oracle's indices must equal the tree's, and the
+    squared distances agree to 1e-5 relative; Chamfer (point-mean + batch-mean of nearest squared distances) likewise."""
+    from scipy.spatial import cKDTree
+    a, b = synth.batch_pairs(77, 2, 4096)
+    k = 16
+    od, oi = strict.knn_points(b, a, k)
+    sep_total = 0
+    for bi in range(2):
+        tree = cKDTree(a[bi].astype(np.float64))
+        dd, ii = tree.query(b[bi].astype(np.float64), k=k + 1)
+        d2 = dd ** 2
+        gaps = np.diff(d2, axis=1)                                       # [S, k]
+        clear = (gaps > 1e-5 * d2[:, 1:] + 1e-9).all(axis=1)            # no near-tie among the first k+1
+        sep_total += int(clear.sum())
+        assert np.array_equal(oi[bi][clear], ii[clear, :k])
+        np.testing.assert_allclose(od[bi][clear], d2[clear, :k], rtol=1e-5, atol=1e-7)
+    assert sep_total > 0.95 * 2 * 4096                                   # the comparison covers nearly every query
+    loss, dx, ix, dy, iy = strict.chamfer(a, b)
+    want = 0.0
+    for bi in range(2):
+        ta, tb = cKDTree(a[bi].astype(np.float64)), cKDTree(b[bi].astype(np.float64))
+        want += (tb.query(a[bi].astype(np.float64))[0] ** 2).mean() + (ta.query(b[bi].astype(np.float64))[0] ** 2).mean()
+    assert abs(loss - want / 2) <= 1e-5 * abs(want / 2)
