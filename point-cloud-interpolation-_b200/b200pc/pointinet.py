@@ -88,7 +88,7 @@ def cuda_backend(tape=None):
     be = types.SimpleNamespace(
         index_points=P.index_points, query_ball_point=P.query_ball_point, knn_point=P.knn_point,
         three_nn_weights=P.three_nn_weights, three_interpolate=P.three_interpolate, group_points=P.group_points,
-        knn_points=S.knn_points, knn_gather=S.knn_gather, tape=tape)
+        knn_points=S.knn_points, knn_gather=S.knn_gather, fusion_group=P.fusion_group, tape=tape)
     if tape is None:
         be.farthest_point_sample = P.farthest_point_sample
         be.sample_points = P.sample_points
@@ -261,6 +261,12 @@ class PointsFusion(nn.Module):
 
     def _neighbours(self, query_cf, ref_cf, ref_feat_cf, k):
         q, r = _rows(query_cf), _rows(ref_cf)
+        fused = getattr(self.be, "fusion_group", None)
+        if fused is not None and k >= 1 and not (torch.is_grad_enabled() and (q.requires_grad or r.requires_grad)):
+            # one C call (direct-form search + one kernel) instead of knn_points, knn_gather, sub, norm, cat and three
+            # permute/contiguous copies (upstream layers.py:346-368); falls through to those for differentiable coordinates
+            feat, nn, extra, _ = fused(q, r, k, _rows(ref_feat_cf))
+            return feat, nn, extra
         res = self.be.knn_points(q, r, K=k, return_nn=True)
         resi = res.knn - q.unsqueeze(2)                                   # [B,N,k,3]
         feat = torch.cat([resi, resi.norm(dim=-1, keepdim=True)], dim=-1)  # + distance channel
