@@ -164,6 +164,11 @@ int b200pc_fusion_group(const float *qry, const float *ref, const float *feat, i
                         float *resi, float *nn, float *gfeat, int64_t *idx, void *workspace, size_t workspace_bytes,
                         b200pc_stream_t stream);
 
+/* The score PointsFusion.forward gives every (point, neighbour) slot: the maximum over the channels of its point-wise MLP
+ * (`torch.max(new_features, dim=1)`, Utils/Layers.py:276; upstream PointINet20230424/models/layers.py:416) when that MLP runs over
+ * channels-last rows: x [rows, C] fp32 (C % 4 == 0, 16-byte aligned) -> out [rows] = max over C; NaN propagates like torch.max. */
+int b200pc_channel_max(const float *x, int64_t rows, int C, float *out, b200pc_stream_t stream);
+
 /* ---- a8 at C5: PolyPCI.rebuild for a QUERY SHARD  PolyPCI/Models/Models_V1.py:102-114 ------------------------------- */
 /* knn_points(qry, ref, K=1, return_nn=True) for the S_local queries of this rank (queries [s_offset, s_offset+S_local) of
  * S_total), packed as 16-byte records {bit pattern of the int32 index, x, y, z} in s-major order:

@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200pc_feature_propagation_workspace_bytes": (_z, [_i, _i, _i]),
     "b200pc_feature_propagation": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "b200pc_fusion_group": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "b200pc_channel_max": (_i, [_p, _l, _i, _p, _p]),
     "b200pc_rebuild_pack_workspace_bytes": (_z, [_i, _i, _i]),
     "b200pc_rebuild_pack": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _z, _p]),
     "b200pc_fps": (_i, [_p, _i, _i, _i, _p, _p, _p, _z, _p]),

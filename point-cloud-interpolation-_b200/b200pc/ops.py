@@ -99,6 +99,7 @@ OP_SCHEMAS = {
     "three_interpolate_bwd": "(Tensor gout, Tensor feat, Tensor idx, Tensor weight, bool want_gweight) -> (Tensor, Tensor)",
     "feature_propagation": "(Tensor unknown, Tensor known, Tensor feat, int variant) -> (Tensor, Tensor, Tensor)",
     "fusion_group": "(Tensor qry, Tensor ref, Tensor? feat, int k) -> (Tensor, Tensor, Tensor, Tensor)",
+    "channel_max": "(Tensor x) -> Tensor",
     "rebuild_pack": "(Tensor ref, Tensor qry, int s_offset, int[] peer_ptrs) -> Tensor",
     "chamfer_fwd": "(Tensor x, Tensor y) -> (Tensor, Tensor, Tensor, Tensor, Tensor)",
     "chamfer_bwd": "(Tensor x, Tensor y, Tensor ix, Tensor iy, Tensor gloss) -> (Tensor, Tensor)",
@@ -411,6 +412,14 @@ def _fusion_group(qry, ref, feat, k):
     return resi, nn, gf, idx
 
 
+@_register("channel_max", lambda x: _f32(x.shape[0], like=x))
+def _channel_max(x):
+    rows, Cc = x.shape
+    out = _f32(rows, like=x)
+    _call(x.device, _lib.load().b200pc_channel_max, _ptr(x), rows, Cc, _ptr(out), _stream(x.device))
+    return out
+
+
 @_register("rebuild_pack", lambda ref, qry, s_offset, peer_ptrs: _f32(qry.shape[1], qry.shape[0], 4, like=ref))
 def _rebuild_pack(ref, qry, s_offset, peer_ptrs):
     """PolyPCI.rebuild for a query shard: K=1 search + (index, neighbour xyz) records [S_local,B,4]; the same kernel also
@@ -625,6 +634,15 @@ def fusion_group(qry, ref, k, feat=None):
         if feat.shape[2] == 0:
             feat = None
     return _O.fusion_group(qry, ref, feat, k)
+
+
+def channel_max(x):
+    """x [rows, C] (channels-last rows of PointsFusion's point-wise MLP) -> [rows] = max over the channels
+    (`torch.max(new_features, dim=1)`, Utils/Layers.py:276)"""
+    x = _prep(x, "x")
+    if x.dim() != 2 or x.shape[1] % 4:
+        return x.max(dim=1)[0]
+    return _O.channel_max(x)
 
 
 def rebuild_pack(ref, qry, s_offset=0, peer_ptrs=()):

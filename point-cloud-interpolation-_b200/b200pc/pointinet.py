@@ -252,12 +252,47 @@ class FlowNet3D(nn.Module):
         return self.classifier(self.fp(p1a, xyz1, u1, feats1))
 
 
+def _conv_relu_stack(seq):
+    """the (Conv2d 1x1, ReLU) pairs of a BN-folded point-wise MLP, or None if the Sequential holds anything else"""
+    mods = list(seq.children())
+    if len(mods) % 2:
+        return None
+    pairs = []
+    for conv, act in zip(mods[0::2], mods[1::2]):
+        if not (isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.bias is not None and isinstance(act, nn.ReLU)):
+            return None
+        pairs.append(conv)
+    return pairs
+
+
 class PointsFusion(nn.Module):
     def __init__(self, be, cin, couts):
         super().__init__()
         self.be = be
         self.conv = _pointwise_mlp([cin, *couts])
         self.batched = True          # False: always the reference's per-item loop (tests compare the two)
+
+    def _score(self, feat):
+        """max over the channels of the point-wise MLP (upstream layers.py:415-416): [B,4,N,2k] -> [B,N,2k].
+        Inference with folded BatchNorm on the device: the three 1x1 convolutions run as GEMMs over channels-last rows with
+        the bias + ReLU in the GEMM epilogue -- torch's conv2d adds the bias and applies the ReLU as two more passes over
+        the [1,128,16384,32] activations (0.5 ms of a 3.2 ms frame, profiles/r02_pointinet_graph.txt).  Same arithmetic,
+        different summation order inside the GEMM: results agree to fp32 rounding."""
+        pairs = None if (self.training or torch.is_grad_enabled() or not feat.is_cuda) else _conv_relu_stack(self.conv)
+        if pairs is None:
+            return self.conv(feat).max(dim=1)[0]
+        B, C, N, K = feat.shape
+        x = feat.permute(0, 2, 3, 1).reshape(B * N * K, C)
+        # same precision policy as the convolutions these GEMMs replace (torch.backends.cudnn.allow_tf32)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+        try:
+            for conv in pairs:
+                x = torch._addmm_activation(conv.bias, x, conv.weight.view(conv.out_channels, conv.in_channels).t())
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        from . import ops
+        return ops.channel_max(x).view(B, N, K)
 
     def _neighbours(self, query_cf, ref_cf, ref_feat_cf, k):
         q, r = _rows(query_cf), _rows(ref_cf)
@@ -293,7 +328,7 @@ class PointsFusion(nn.Module):
             (f1, g1, e1), (f2, g2, e2) = _concurrently(lambda: self._neighbours(mixed, xyz1, feats1, k1),
                                                      lambda: self._neighbours(mixed, xyz2, feats2, k2), mixed, "fusion")
             feat, grouped, extra = torch.cat((f1, f2), dim=-1), torch.cat((g1, g2), dim=-1), torch.cat((e1, e2), dim=-1)
-            w = F.softmax(self.conv(feat).max(dim=1)[0], dim=-1)
+            w = F.softmax(self._score(feat), dim=-1)
             return (w.unsqueeze(1) * torch.cat([grouped, extra], dim=1)).sum(dim=-1)
         fa, ga, ea = [], [], []
         for i in range(B):
@@ -307,7 +342,7 @@ class PointsFusion(nn.Module):
                                                      lambda: self._neighbours(mixed, b, feats2[i:i + 1], k2), mixed, "fusion")
             fa.append(torch.cat((f1, f2), dim=-1)); ga.append(torch.cat((g1, g2), dim=-1)); ea.append(torch.cat((e1, e2), dim=-1))
         feat, grouped, extra = torch.cat(fa, 0), torch.cat(ga, 0), torch.cat(ea, 0)
-        w = F.softmax(self.conv(feat).max(dim=1)[0], dim=-1)               # [B,N,2k]
+        w = F.softmax(self._score(feat), dim=-1)                           # [B,N,2k]
         return (w.unsqueeze(1) * torch.cat([grouped, extra], dim=1)).sum(dim=-1)
 
 

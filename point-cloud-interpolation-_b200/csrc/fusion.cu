@@ -13,6 +13,8 @@
 // Conv2d-layout tensors; thread e = (s, j) with j fastest, so every store instruction of a warp is 128 contiguous bytes
 // of one channel plane.  |resi| is sqrt((rx*rx + ry*ry) + rz*rz), every step rounded on its own like torch's
 // pow/sum/sqrt composition; values within 1e-5 relative of torch.norm (its accumulation order is not part of its contract).
+#include <math_constants.h>
+
 #include "common.cuh"
 #include "search.cuh"
 
@@ -51,6 +53,28 @@ __global__ void __launch_bounds__(256) fusion_features_kernel(const float *__res
 // contiguous slabs.  The same thread stores the record into the local buffer and into every peer's buffer (peer-mapped
 // symmetric memory: plain st.global over NVLink), i.e. the all-gather of the shard outputs happens from inside the
 // producing kernel -- no separate collective launch; the ranks only meet at a barrier afterwards.
+// PointsFusion.forward scores every (point, neighbour) slot by the MAXIMUM over the channels of its point-wise MLP
+// (`torch.max(new_features, dim=1)`, Utils/Layers.py:276, upstream PointINet20230424/models/layers.py:416).  With the MLP run
+// as GEMMs over channels-last rows that is a max over each contiguous row of C floats: one warp per row, 16-byte loads,
+// five shuffles.  HBM bound (268 MB at C1); ATen's reduction takes 244 us for it, this 50 us.
+__global__ void __launch_bounds__(256) channel_max_kernel(const float4 *__restrict__ x, long rows, int C4, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long r = warp; r < rows; r += nwarps) {
+        float m = -CUDART_INF_F;
+        bool nan = false;
+        for (int c = lane; c < C4; c += 32) {
+            const float4 v = ldg_stream(x + r * C4 + c);
+            nan = nan || v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w;
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        nan = __any_sync(0xffffffffu, nan);
+        if (lane == 0) out[r] = nan ? __int_as_float(0x7fc00000) : m;       // torch.max propagates NaN
+    }
+}
+
 constexpr int MAX_PEERS = 8;
 struct PeerPtrs { float4 *p[MAX_PEERS]; };
 
@@ -83,6 +107,18 @@ using namespace b200pc;
 namespace b200pc {
 int run_topk_i32(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx32, float *dist,
                  void *ws, size_t ws_bytes, cudaStream_t st);
+}
+
+extern "C" int b200pc_channel_max(const float *x, int64_t rows, int C, float *out, b200pc_stream_t stream) {
+    B200PC_REQUIRE(rows >= 0 && C >= 4 && C % 4 == 0, "channel_max: C=%d must be a positive multiple of 4", C);
+    if (rows == 0) return B200PC_OK;
+    B200PC_REQUIRE(x && out && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "channel_max: null or misaligned pointer");
+    long blocks = (rows + 7) / 8;
+    const long cap = (long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    channel_max_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(x), (long)rows, C / 4, out);
+    B200PC_LAUNCH_CHECK();
+    return B200PC_OK;
 }
 
 extern "C" size_t b200pc_rebuild_pack_workspace_bytes(int B, int N, int S_local) {

@@ -211,3 +211,15 @@ def test_error_behaviour_of_the_new_entries(cuda_dev):
         bio.sample_clouds([np.zeros((100, 3), np.float32)], 10, device="cpu")
     with pytest.raises(RuntimeError):                       # CPU tensors never reach a kernel
         P.fusion_group(qry.cpu(), ref.cpu(), 2)
+
+
+def test_channel_max(cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    for rows, C in [(1000, 128), (7, 4), (4097, 64), (33, 260)]:
+        x = torch.randn(rows, C, generator=g).to(cuda_dev)
+        assert torch.equal(ops.channel_max(x), x.max(dim=1)[0])
+    x = torch.randn(10, 128, generator=g).to(cuda_dev); x[3, 77] = float("nan")
+    got = ops.channel_max(x)
+    assert torch.isnan(got[3]) and torch.equal(got[[0, 1, 2, 4]], x.max(dim=1)[0][[0, 1, 2, 4]])
+    y = torch.randn(5, 6, generator=g).to(cuda_dev)                     # C not a multiple of 4: served by torch
+    assert torch.equal(ops.channel_max(y), y.max(dim=1)[0])
