@@ -61,6 +61,7 @@ static void load_tuning() {
     t.interp_flat = env_int("B200PC_INTERP_FLAT", -1);
     t.bulk = env_int("B200PC_BULK", -1);
     t.fps_cluster = env_int("B200PC_FPS_CLUSTER", 0);
+    t.fps_flat = env_int("B200PC_FPS_FLAT", -1);
     t.drain = env_int("B200PC_DRAIN", -1);
     t.grid = env_int("B200PC_GRID", 1);
     g_tuning = t;

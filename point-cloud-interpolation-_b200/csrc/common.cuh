@@ -49,6 +49,7 @@ struct Tuning {
     int gather_rows, gather_flat, interp_rows, interp_flat;
     int bulk;                                // 0: register-path row movers (gather.cu / group.cu) instead of rowmove.cu
     int fps_cluster;
+    int fps_flat;                            // 0: two-level arg-max (block, then cluster records); 1: flat exchange of warp keys; -1: by cluster size
     int drain;                               // search drain variant (A/B)
     int grid;                                // 0: top-k searches start from tau = +inf; 1: default (warm start when worth it); 2: always
 };
@@ -153,6 +154,12 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar_cluster) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster),
                  "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar_cluster)
+                 : "memory");
+}
+// 8-byte asynchronous store into a peer CTA's shared memory (same completion mechanism)
+__device__ __forceinline__ void st_async_b64(uint32_t dst_cluster, unsigned long long v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster), "l"(v),
+                 "r"(bar_cluster)
                  : "memory");
 }
 // wait with cluster-scope acquire: data written by peers with st.async is visible afterwards

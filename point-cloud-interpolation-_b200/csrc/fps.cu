@@ -178,6 +178,138 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
     if (C > 1) cluster.sync();  // nobody exits while a peer may still write into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Flat variant (round 2).  The two-level arg-max above costs, per round, a block barrier plus a second exchange stage:
+// ~340 cycles of block reduction and 600-750 of record exchange on top of an ~100-cycle update.  Here every WARP sends its
+// 8-byte key (max bits << 32 | ~index) straight to all CTAs of the cluster with st.async (one lane per destination); the
+// bytes complete on each receiver's mbarrier, every warp then reduces the C*16 keys itself (4 per lane + two REDUX), and the
+// winner's coordinates come from a copy of the WHOLE cloud that every CTA keeps in shared memory (N <= 16 384; larger
+// clouds read them from global memory).  No __syncthreads in the loop, one cluster-wide dependency per round.
+// It did NOT turn out uniformly faster: the st.async -> mbarrier -> wake path costs ~700 cycles even inside one CTA, so
+// the launcher uses it only for 4-CTA clusters (see b200pc_fps).
+// Arithmetic, tie rule and padding are those of fps_kernel: the picks are identical.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FPS_FULL_COPY_MAX = 16384;      // points whose xyz fit beside the keys in one CTA's shared memory (196 608 bytes)
+
+template <int P>
+__global__ void __launch_bounds__(FPS_T) fps_flat_kernel(const float *__restrict__ xyz, int N, int npoint,
+                                                         const int64_t *__restrict__ start, int64_t *__restrict__ out, int full_copy) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cta_base = rank * (FPS_T * P);
+    const int W = C * FPS_WARPS;                                       // warps of the cluster = keys per round
+    const int gwid = rank * FPS_WARPS + warp;
+
+    extern __shared__ __align__(16) float fps_smem[];                 // full_copy: xyz of the whole cloud, [N][3]
+    __shared__ __align__(8) unsigned long long keys[2][FPS_MAX_CLUSTER * FPS_WARPS];   // per parity: one key per warp of the cluster
+    __shared__ __align__(8) unsigned long long xbar[2];
+
+    const float *cloud = xyz + (size_t)b * N * 3;
+    float x[P], y[P], z[P], mind[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int i = cta_base + p * FPS_T + t;
+        if (i < N) {
+            x[p] = cloud[i * 3 + 0]; y[p] = cloud[i * 3 + 1]; z[p] = cloud[i * 3 + 2];
+            mind[p] = 1e10f;
+        } else {  // padding: min-dist 0 loses every tie because its index is larger than any real one
+            x[p] = 0.f; y[p] = 0.f; z[p] = 0.f; mind[p] = 0.f;
+        }
+    }
+    if (full_copy)
+        for (int i = t; i < N * 3; i += FPS_T) fps_smem[i] = cloud[i];
+    if (t == 0) {
+        mbar_init(smem_u32(&xbar[0]), 1); mbar_init(smem_u32(&xbar[1]), 1);
+        mbar_fence_init();
+    }
+    int far = (int)start[b];
+    far = far < 0 ? 0 : (far >= N ? N - 1 : far);      // a bad start index must not read outside the cloud
+    float cx = cloud[far * 3 + 0], cy = cloud[far * 3 + 1], cz = cloud[far * 3 + 2];
+    cluster.sync();                                     // barriers initialised and copies visible everywhere
+
+    for (int it = 0; it < npoint; ++it) {
+        if (rank == 0 && t == 0) out[(size_t)b * npoint + it] = far;
+        if (it == npoint - 1) break;  // the last pick needs no further update
+
+        // ---- running-min update, reference rounding order (every product rounded on its own: see fps_kernel) ----
+        float lmax = 0.f;
+        if (P >= 2) {
+            const f32x2 ncx = splat2(-cx), ncy = splat2(-cy), ncz = splat2(-cz);
+#pragma unroll
+            for (int p = 0; p < P; p += 2) {
+                const f32x2 dx = add2(pack2(x[p], x[p + 1]), ncx);
+                const f32x2 dy = add2(pack2(y[p], y[p + 1]), ncy);
+                const f32x2 dz = add2(pack2(z[p], z[p + 1]), ncz);
+                float ax, bx, ay, by, az, bz;
+                unpack2(dx, ax, bx); unpack2(dy, ay, by); unpack2(dz, az, bz);
+                const float d0 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+                const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz));
+                mind[p] = fminf(mind[p], d0);
+                mind[p + 1] = fminf(mind[p + 1], d1);
+                lmax = fmaxf(lmax, fmaxf(mind[p], mind[p + 1]));
+            }
+        } else {
+            const float dx = __fadd_rn(x[0], -cx), dy = __fadd_rn(y[0], -cy), dz = __fadd_rn(z[0], -cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            mind[0] = fminf(mind[0], d);
+            lmax = mind[0];
+        }
+        int lp = 0;
+#pragma unroll
+        for (int p = P - 1; p >= 0; --p)
+            if (mind[p] == lmax) lp = p;                       // first local point attaining the local max
+        const unsigned int lbits = __float_as_uint(lmax);      // min-dists are >= +0: their bits order like unsigned ints
+        const unsigned int linv = 0xffffffffu - (unsigned int)(cta_base + lp * FPS_T + t);   // larger = lower index
+        const unsigned int wbits = __reduce_max_sync(0xffffffffu, lbits);
+        const unsigned int winv = __reduce_max_sync(0xffffffffu, lbits == wbits ? linv : 0u);
+
+        // ---- flat exchange: this warp's key goes to every CTA of the cluster; bytes complete on the receiver's barrier ----
+        const int par = it & 1;
+        const uint32_t my_bar = smem_u32(&xbar[par]);
+        if (t == 0) mbar_expect_tx(my_bar, (uint32_t)(W * 8));             // W keys of 8 bytes will land here this round
+        if (lane < C)
+            st_async_b64(map_to_rank(smem_u32(&keys[par][gwid]), (uint32_t)lane), ((unsigned long long)wbits << 32) | winv,
+                         map_to_rank(my_bar, (uint32_t)lane));
+        mbar_wait_cluster(my_bar, (uint32_t)((it >> 1) & 1));
+        unsigned int kb = 0u, ki = 0u;
+        for (int j = lane; j < W; j += 32) {
+            const unsigned long long k = keys[par][j];
+            const unsigned int hb = (unsigned int)(k >> 32), lo = (unsigned int)k;
+            if (hb > kb || (hb == kb && lo > ki)) { kb = hb; ki = lo; }
+        }
+        const unsigned int bb = __reduce_max_sync(0xffffffffu, kb);
+        const unsigned int bi = __reduce_max_sync(0xffffffffu, kb == bb ? ki : 0u);
+        far = (int)(0xffffffffu - bi);
+        if (full_copy) { cx = fps_smem[far * 3 + 0]; cy = fps_smem[far * 3 + 1]; cz = fps_smem[far * 3 + 2]; }
+        else { cx = __ldg(cloud + far * 3 + 0); cy = __ldg(cloud + far * 3 + 1); cz = __ldg(cloud + far * 3 + 2); }
+    }
+    cluster.sync();  // nobody exits while a peer may still write into its shared memory
+}
+
+template <int P>
+static int launch_fps_flat(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, int C,
+                           cudaStream_t st) {
+    auto kern = fps_flat_kernel<P>;
+    const int full_copy = N <= FPS_FULL_COPY_MAX;
+    const size_t smem = full_copy ? (size_t)N * 3 * sizeof(float) : 16;
+    B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) B200PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, B, 1);
+    cfg.blockDim = dim3(FPS_T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    B200PC_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, idx, full_copy));
+    return B200PC_OK;
+}
+
 template <int P>
 static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx, int C,
                       cudaStream_t st) {
@@ -234,6 +366,19 @@ extern "C" int b200pc_fps(const float *xyz, int B, int N, int npoint, const int6
     int C, P;
     fps_shape(B, N, &C, &P);
     cudaStream_t st = as_stream(stream);
+    // Measured at 16 384 points (tools/fps_sweep.py, us per round, two-level / flat): C=2 0.98 / 1.05, C=4 0.75 / 0.67,
+    // C=8 0.62 / 0.68, C=16 0.63 / 0.94; one CTA 0.29 / 0.50.  The flat exchange wins exactly where the cluster is 4 CTAs
+    // (batches of >= 10 clouds, e.g. C3: 3.05 -> 2.70 ms); everywhere else the two-level kernel stays.
+    const int flat = tuning().fps_flat;
+    if (flat > 0 || (flat < 0 && C == 4)) {
+        switch (P) {
+            case 1: return launch_fps_flat<1>(xyz, B, N, npoint, start, idx, C, st);
+            case 2: return launch_fps_flat<2>(xyz, B, N, npoint, start, idx, C, st);
+            case 4: return launch_fps_flat<4>(xyz, B, N, npoint, start, idx, C, st);
+            case 8: return launch_fps_flat<8>(xyz, B, N, npoint, start, idx, C, st);
+            default: return launch_fps_flat<16>(xyz, B, N, npoint, start, idx, C, st);
+        }
+    }
     switch (P) {
         case 1: return launch_fps<1>(xyz, B, N, npoint, start, idx, C, st);
         case 2: return launch_fps<2>(xyz, B, N, npoint, start, idx, C, st);

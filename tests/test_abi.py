@@ -66,8 +66,8 @@ def test_fps_kernels_never_fuse_multiply_add():
     """farthest_point_sample computes (dx*dx + dy*dy) + dz*dz with every product rounded on its own
     (Utils/Pointnet2Utils.py:80).  ptxas 12.9 contracts packed mul+add into FFMA2, so the kernel spells the
     products with scalar .rn intrinsics; any fused multiply-add in its SASS would flip near-tied picks."""
-    funcs = {n: b for n, b in _sass_by_function().items() if "fps_kernel" in n}
-    assert len(funcs) == 5, sorted(funcs)
+    funcs = {n: b for n, b in _sass_by_function().items() if "fps_kernel" in n or "fps_flat_kernel" in n}
+    assert len(funcs) == 10, sorted(funcs)          # two kernel families x P = 1, 2, 4, 8, 16
     for name, body in funcs.items():
         text = "\n".join(body)
         for bad in ("FFMA2", "FMUL2", " FFMA ", "FFMA.", "DFMA"):

@@ -38,8 +38,11 @@ FPS_CASES = [(1, 16384, 1024), (2, 1024, 256), (2, 256, 64), (3, 64, 16), (1, 81
              (2, 5000, 500), (1, 40000, 256), (1, 70000, 128), (16, 16384, 64), (1, 3, 3)]
 
 
+@pytest.mark.parametrize("flat", ["auto", "0", "1"])      # two-level arg-max / flat exchange of warp keys / launcher's choice
 @pytest.mark.parametrize("B,N,npoint", FPS_CASES)
-def test_fps_bit_exact(cuda_dev, B, N, npoint):
+def test_fps_bit_exact(cuda_dev, monkeypatch, B, N, npoint, flat):
+    if flat != "auto":
+        monkeypatch.setenv("B200PC_FPS_FLAT", flat); ops.reload_tuning()
     a, _ = synth.batch_pairs(70, B, N)
     start = np.random.default_rng(N).integers(0, N, size=B)
     out = P.farthest_point_sample_from(_t(a, cuda_dev), npoint, _t(start, cuda_dev))
@@ -56,8 +59,10 @@ def test_fps_duplicates_first_argmax(cuda_dev):
     np.testing.assert_array_equal(out.cpu().numpy(), strict.farthest_point_sample(dup, 2500, start))
 
 
+@pytest.mark.parametrize("flat", ["0", "1"])
 @pytest.mark.parametrize("N", [301, 1025, 2049, 4097, 8193, 16385, 40001])     # P = 1, 2, 4, 8, 16 and clusters of 2..8 CTAs
-def test_fps_near_ties_no_fused_multiply_add(cuda_dev, N):
+def test_fps_near_ties_no_fused_multiply_add(cuda_dev, monkeypatch, N, flat):
+    monkeypatch.setenv("B200PC_FPS_FLAT", flat); ops.reload_tuning()
     """clouds built so that fma(dz,dz,fma(dy,dy,dx*dx)) picks a different point than the reference's
     (dx*dx + dy*dy) + dz*dz already in the first round (tests/adversarial.py)"""
     from adversarial import fps_rot90_cloud, first_round_pick
