@@ -92,18 +92,27 @@ __global__ void __launch_bounds__(GR_MAX_WARPS * 32, 1) group_async_kernel(const
         // ---- the unit's index block idx[b, s0..s0+31, k0..k0+nk) -> shared as row numbers b*N + i (-1: none) ----
         __syncwarp();
         {
-            int sl = 0, kk = lane;
-            while (kk >= nk) { kk -= nk; ++sl; }
-            while (sl < 32) {
-                int r = -1;
-                if (s0 + sl < S) {
-                    long i = idx[((size_t)b * S + s0 + sl) * K + k0 + kk];
-                    if (i < 0) i += N;
-                    if (i >= 0 && i < N) r = b * N + (int)i;
+            // element e = sl * nk + kk of the block, 32 per pass (coalesced over (s, k)); all loads of the block are issued
+            // before the first store so that they overlap (the block is the head of the unit's dependent chain)
+            const int total = 32 * nk;
+            for (int e0 = 0; e0 < total; e0 += 128) {
+                long iv[4];
+                int ee[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ee[u] = e0 + 32 * u + lane;
+                    const int sl = ee[u] / nk, kk = ee[u] - sl * nk;
+                    iv[u] = (ee[u] < total && s0 + sl < S) ? idx[((size_t)b * S + s0 + sl) * K + k0 + kk] : (long)N;
                 }
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(ibuf + (uint32_t)sl * idx_stride + 4u * kk), "r"(r) : "memory");
-                kk += 32;
-                while (kk >= nk) { kk -= nk; ++sl; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ee[u] >= total) continue;
+                    const int sl = ee[u] / nk, kk = ee[u] - sl * nk;
+                    long i = iv[u];
+                    if (i < 0) i += N;
+                    const int r = (i >= 0 && i < N) ? b * N + (int)i : -1;
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ibuf + (uint32_t)sl * idx_stride + 4u * kk), "r"(r) : "memory");
+                }
             }
         }
         __syncwarp();
@@ -140,15 +149,20 @@ __global__ void __launch_bounds__(GR_MAX_WARPS * 32, 1) group_async_kernel(const
         int st = 0;
         float *o = out + ((size_t)b * C * K + k0) * S + s;
         for (int kk = 0; kk < nk; ++kk, o += S) {
-            issue(kk + NST - 1, st == 0 ? NST - 1 : st - 1);         // into the stage consumed one iteration ago
+            // the xyz row (12 bytes, through the LSU) is requested BEFORE the feature rows are issued: its latency hides behind
+            // the copy loop instead of stalling the warp in front of it
             const int r = row_of(lane, kk);
             const bool ok = r >= 0;
-            // xyz channels through the LSU while the feature rows are (still) in flight
+            float px = 0.0f, py = 0.0f, pz = 0.0f;
+            if (live && ok) {
+                const float *xr = xyz + (size_t)r * 3;
+                px = __ldg(xr + 0); py = __ldg(xr + 1); pz = __ldg(xr + 2);
+            }
+            issue(kk + NST - 1, st == 0 ? NST - 1 : st - 1);         // into the stage consumed one iteration ago
             if (live) {
-                const float *xr = xyz + (size_t)(ok ? r : 0) * 3;
-                __stcs(o + (size_t)(xoff + 0) * cstride, __fsub_rn(ok ? __ldg(xr + 0) : 0.0f, cx));
-                __stcs(o + (size_t)(xoff + 1) * cstride, __fsub_rn(ok ? __ldg(xr + 1) : 0.0f, cy));
-                __stcs(o + (size_t)(xoff + 2) * cstride, __fsub_rn(ok ? __ldg(xr + 2) : 0.0f, cz));
+                __stcs(o + (size_t)(xoff + 0) * cstride, __fsub_rn(px, cx));
+                __stcs(o + (size_t)(xoff + 1) * cstride, __fsub_rn(py, cy));
+                __stcs(o + (size_t)(xoff + 2) * cstride, __fsub_rn(pz, cz));
             }
             cp_async_wait<NST - 1>();                                 // tile kk has landed (this lane's share)
             __syncwarp();                                             // ... every lane's share
