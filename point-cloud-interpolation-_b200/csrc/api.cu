@@ -64,6 +64,7 @@ static void load_tuning() {
     t.fps_flat = env_int("B200PC_FPS_FLAT", -1);
     t.drain = env_int("B200PC_DRAIN", -1);
     t.grid = env_int("B200PC_GRID", 1);
+    t.seed = env_int("B200PC_SEED", 0);
     g_tuning = t;
     g_tuning_loaded = true;
 }

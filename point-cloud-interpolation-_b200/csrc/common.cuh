@@ -51,6 +51,7 @@ struct Tuning {
     int fps_cluster;
     int fps_flat;                            // 0: two-level arg-max (block, then cluster records); 1: flat exchange of warp keys; -1: by cluster size
     int drain;                               // search drain variant (A/B)
+    int seed;                                // 1 (default): warm start from the k-th distance inside the query's cell box; 0: from the box's farthest corner
     int grid;                                // 0: top-k searches start from tau = +inf; 1: default (warm start when worth it); 2: always
 };
 const Tuning &tuning();

@@ -75,9 +75,9 @@ __device__ __forceinline__ int slot_to_ref(int s, int strided, int n_tiles) {
 static_assert(TILE == 512, "slot_to_ref assumes 512-slot tiles");
 
 struct GridDesc;
-__device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G);
-__device__ __forceinline__ void grid_count(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z);
+__device__ __forceinline__ void grid_count_ref(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z);
 
+// grid != null: also count the ref into the occupancy grid (section 1b, the variant without sorting)
 __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad, int strided, float4 *__restrict__ packed,
                                  const GridDesc *__restrict__ grid, unsigned *__restrict__ counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
@@ -91,7 +91,7 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
         if (i < N) {
             x[h] = r[i * 3 + 0]; y[h] = r[i * 3 + 1]; z[h] = r[i * 3 + 2];
             w[h] = filter_norm(torch_sq_norm(x[h], y[h], z[h]));
-            if (grid) grid_count(grid, counts, b, x[h], y[h], z[h]);
+            if (grid) grid_count_ref(grid, counts, b, x[h], y[h], z[h]);
         } else {
             // padding: the filter sees u = +inf or NaN (never a hit); every exact form gives +inf or NaN (never selected)
             x[h] = CUDART_INF_F; y[h] = 0.0f; z[h] = 0.0f; w[h] = CUDART_INF_F;
@@ -108,25 +108,28 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1b. occupancy grid: a conservative STARTING threshold for the top-k searches
+// 1b. occupancy grid: cell-sorted refs and queries, and a STARTING threshold for the top-k searches
 // ---------------------------------------------------------------------------------------------
 // A streaming k-best that starts from tau = +inf pays k(1 + ln(N/k)) heap inserts per query (127 at C2), more than half of
 // them in the first tile, and in lock-step a warp pays the maximum over its lanes (profiles/r01_notes.md: the drain is
-// 50 % of the kernel).  Nothing forces the search to start blind: any radius that provably holds >= k refs bounds the
-// k-th distance.  The refs are counted into a coarse uniform grid (one atomicAdd per ref inside pack_refs_kernel, <= 128
-// cells along the longest axis of their bounding box); a query looks at the counts of the cell box of half-width rho = 0,
-// 1, 2, 3 around its own cell and takes the first box holding >= k refs: every ref of that box is closer than the box's
-// farthest corner, so   tau0 = |q - farthest corner|^2 (1 + 1e-5) + 16 eps (|q|^2 + max|r|^2)
-// is an upper bound of the k-th smallest distance IN THE REFERENCE'S ROUNDING (the second term covers the rounding error
-// of the expanded forms, <= 10.02 eps (|q|^2 + |r|^2)).  Every (query, ref) pair still goes through the
-// filter -- this is brute force with a warm start, and since tau0 is only ever an upper bound the results are
-// bit-identical; at C2 it cuts the inserts per query from 127 to ~45.  Queries with non-finite coordinates, clouds with
-// fewer than k finite refs and boxes that stay short of k refs start from +inf (or the whole bounding box) like before.
+// 50 % of the kernel).  Nothing forces the search to start blind, or to visit the points in the caller's order:
+//   * the refs are counted into a uniform grid over their bounding box (<= 128 cells along the longest axis, <= 131072
+//     cells) with a pyramid of four coarser levels, and SORTED by cell (counting sort: count, scan, scatter).  The tiles of
+//     the search are cut from the sorted order, so the refs near a query sit in a handful of tiles;
+//   * the queries are sorted by the cell of the same grid they fall into, so the 32 queries of a warp are neighbours in
+//     space: their candidates come in the same few tiles and in similar numbers (the lock-step drain stops idling);
+//   * every query starts from tau0 = (an upper bound of) the k-th smallest distance to the refs of the first cell box
+//     around it that holds >= k refs (grid_seed_kernel).
+// Every (query, ref) pair still goes through the filter -- this is brute force in a different visiting order with a warm
+// start; tau0 is only ever an upper bound and the heap's (distance, index) keys do not depend on the visiting order, so the
+// results are bit-identical.  Outputs are written to the rows of the caller's query order.
 constexpr int GRID_AXIS = 128;             // cells along the longest axis (level 0)
 constexpr int GRID_MAX_CELLS = 131072;     // level-0 cells per batch item
 constexpr int GRID_LEVELS = 5;             // level l has cells of size h * 2^l (a count pyramid)
 constexpr int GRID_STRIDE = 176128;        // counters per batch item: 131072 + 32768 + 8192 + 2048 + 512 rounded up (688 KB)
+constexpr int GRID_SEGS = GRID_MAX_CELLS / 1024;
 constexpr long GRID_MIN_PAIRS = 1L << 24;  // searches smaller than this start blind (the grid would cost more than it saves)
+constexpr long GRID_SORT_MIN_PAIRS = 1L << 30;   // and smaller than this do not sort
 
 struct GridDesc {            // one per batch item, written by grid_bbox_kernel
     float lo[3], hi[3];      // bounding box of the finite refs
@@ -140,17 +143,51 @@ struct GridDesc {            // one per batch item, written by grid_bbox_kernel
 static_assert(sizeof(GridDesc) == 128, "GridDesc is 128 bytes");
 static_assert(GRID_STRIDE % 4096 == 0, "counters are zeroed 16 bytes at a time");
 
+// Workspace of the grid path, per search call (B batch items).  Everything between `counts` and `tail` is zeroed by ONE memset.
+struct GridBufs {
+    GridDesc *desc;          // [B]
+    unsigned *counts;        // [B][GRID_STRIDE]     refs per cell, all levels
+    unsigned *qcend;         // [B][GRID_MAX_CELLS]  queries per level-0 cell, then (in place) the running end of each cell's range
+    unsigned *tail;          // [B]                  non-finite refs placed so far (they go behind the finite ones)
+    unsigned *cend;          // [B][GRID_MAX_CELLS]  refs: start, then end of each level-0 cell's range in the sorted order
+    unsigned *seg, *qseg;    // [B][GRID_SEGS]       counts per 1024-cell segment (refs, queries)
+    float4 *sorted;          // [B][N]   refs in cell order {x, y, z, index}
+    float4 *qsorted;         // [B][S]   queries in cell order {x, y, z, index}
+    int *perm;               // [B][n_pad]  sorted slot -> ref index
+    float *seed;             // [B][S]   starting thresholds, in the sorted query order
+};
+static size_t grid_layout(int B, int N, int S, int n_pad, char *base, GridBufs *g) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += align_up(bytes, 256); return p; };
+    GridDesc *desc = reinterpret_cast<GridDesc *>(take((size_t)B * sizeof(GridDesc)));
+    unsigned *counts = reinterpret_cast<unsigned *>(take((size_t)B * GRID_STRIDE * sizeof(unsigned)));
+    unsigned *qcend = reinterpret_cast<unsigned *>(take((size_t)B * GRID_MAX_CELLS * sizeof(unsigned)));
+    unsigned *tail = reinterpret_cast<unsigned *>(take((size_t)B * sizeof(unsigned)));
+    unsigned *cend = reinterpret_cast<unsigned *>(take((size_t)B * GRID_MAX_CELLS * sizeof(unsigned)));
+    unsigned *seg = reinterpret_cast<unsigned *>(take((size_t)B * GRID_SEGS * sizeof(unsigned)));
+    unsigned *qseg = reinterpret_cast<unsigned *>(take((size_t)B * GRID_SEGS * sizeof(unsigned)));
+    float4 *sorted = reinterpret_cast<float4 *>(take((size_t)B * N * sizeof(float4)));
+    float4 *qsorted = reinterpret_cast<float4 *>(take((size_t)B * S * sizeof(float4)));
+    int *perm = reinterpret_cast<int *>(take((size_t)B * n_pad * sizeof(int)));
+    float *seed = reinterpret_cast<float *>(take((size_t)B * S * sizeof(float)));
+    if (g) *g = GridBufs{desc, counts, qcend, tail, cend, seg, qseg, sorted, qsorted, perm, seed};
+    return o;
+}
+
 __device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G) {
     const float f = (v - lo) * inv_h;
     int c = f > 0.0f ? (int)fminf(f, 1.0e6f) : 0;      // NaN -> 0
     return c < G ? c : G - 1;
 }
+__device__ __forceinline__ int grid_cell_index(const GridDesc &g, float x, float y, float z) {
+    const int cx = grid_cell(x, g.lo[0], g.inv_h, g.dim[0][0]), cy = grid_cell(y, g.lo[1], g.inv_h, g.dim[0][1]),
+              cz = grid_cell(z, g.lo[2], g.inv_h, g.dim[0][2]);
+    return (cz * g.dim[0][1] + cy) * g.dim[0][0] + cx;
+}
 
-__global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict__ ref, int N, GridDesc *__restrict__ desc,
-                                                         unsigned *__restrict__ counts) {
+__global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict__ ref, int N, GridDesc *__restrict__ desc) {
     const int b = blockIdx.x;
     const float *r = ref + (size_t)b * N * 3;
-    (void)counts;                                             // zeroed by a memset node before this kernel (a block per cloud is too few to do it here)
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     int nf = 0;
     for (int i0 = threadIdx.x; i0 < N; i0 += 4 * blockDim.x) {          // four points per thread in flight
@@ -227,84 +264,165 @@ __global__ void __launch_bounds__(1024) grid_bbox_kernel(const float *__restrict
             d.off[l] = off;
             off += d.dim[l][0] * d.dim[l][1] * d.dim[l][2];
         }
-        if (off > GRID_STRIDE) d.n_finite = 0;               // cannot happen for dims <= 128 and <= 131072 cells; if it did: start blind
         d.pad[0] = d.pad[1] = 0;
         desc[b] = d;
     }
 }
 
-__device__ __forceinline__ void grid_count(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z) {
-    if (!(isfinite(x) && isfinite(y) && isfinite(z))) return;
-    const GridDesc &g = desc[b];
-    if (g.n_finite <= 0) return;
-    const int cx = grid_cell(x, g.lo[0], g.inv_h, g.dim[0][0]), cy = grid_cell(y, g.lo[1], g.inv_h, g.dim[0][1]),
-              cz = grid_cell(z, g.lo[2], g.inv_h, g.dim[0][2]);
-    atomicAdd(counts + (size_t)b * GRID_STRIDE + ((size_t)cz * g.dim[0][1] + cy) * g.dim[0][0] + cx, 1u);
+__device__ __forceinline__ void grid_count_ref(const GridDesc *desc, unsigned *counts, int b, float x, float y, float z) {
+    if (isfinite(x) && isfinite(y) && isfinite(z)) atomicAdd(counts + (size_t)b * GRID_STRIDE + grid_cell_index(desc[b], x, y, z), 1u);
 }
 
-// the coarser levels: every occupied level-0 cell adds its count to its ancestors (a few thousand atomics per cloud;
-// counting all five levels per ref inside pack_refs_kernel instead tripled that kernel's time: the coarse cells contend)
-__global__ void __launch_bounds__(256) grid_pyramid_kernel(const GridDesc *__restrict__ desc, unsigned *__restrict__ counts) {
-    const int b = blockIdx.y;
+// one atomic per point: refs (finite ones) into counts, queries (clamped into the border cells; NaN -> cell 0) into qcend
+__global__ void __launch_bounds__(256) grid_count_kernel(const float *__restrict__ ref, int N, const float *__restrict__ qry, int S,
+                                                         const GridDesc *__restrict__ desc, unsigned *__restrict__ counts,
+                                                         unsigned *__restrict__ qcend) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= N + S) return;
     const GridDesc &g = desc[b];
-    if (g.n_finite <= 0) return;
+    const float *p = i < N ? ref + ((size_t)b * N + i) * 3 : qry + ((size_t)b * S + (i - N)) * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    if (i < N) {
+        if (isfinite(x) && isfinite(y) && isfinite(z)) atomicAdd(counts + (size_t)b * GRID_STRIDE + grid_cell_index(g, x, y, z), 1u);
+    } else {
+        atomicAdd(qcend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
+    }
+}
+
+// blockIdx.z = 0: the coarser levels of the ref counts -- every occupied level-0 cell adds its count to its ancestors (a
+// few thousand atomics per cloud; counting all five levels per ref tripled the counting kernel's time: the coarse cells
+// contend).  Block x owns the cells [1024 x, 1024 x + 1024) and leaves their total in seg[b][x] for grid_scan_kernel.
+// blockIdx.z = 1: only the segment totals, of the query counts.
+__global__ void __launch_bounds__(256) grid_pyramid_kernel(const GridDesc *__restrict__ desc, unsigned *__restrict__ counts,
+                                                           unsigned *__restrict__ seg, const unsigned *__restrict__ qcend,
+                                                           unsigned *__restrict__ qseg) {
+    const int b = blockIdx.y;
+    const bool refs = blockIdx.z == 0;
+    const GridDesc &g = desc[b];
     const int cells = g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
     unsigned *base = counts + (size_t)b * GRID_STRIDE;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
-        const unsigned n = base[c];
-        if (n == 0) continue;
+    const unsigned *src = refs ? base : qcend + (size_t)b * GRID_MAX_CELLS;
+    unsigned sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = blockIdx.x * 1024 + i * 256 + threadIdx.x;
+        const unsigned n = c < cells ? src[c] : 0u;
+        sum += n;
+        if (n == 0 || !refs) continue;
         const int cx = c % g.dim[0][0], cy = (c / g.dim[0][0]) % g.dim[0][1], cz = c / (g.dim[0][0] * g.dim[0][1]);
 #pragma unroll
         for (int l = 1; l < GRID_LEVELS; ++l)
             atomicAdd(base + g.off[l] + (((cz >> l) * g.dim[l][1] + (cy >> l)) * g.dim[l][0] + (cx >> l)), n);
     }
-}
-
-// refs counted in the 3 x 3 x 3 box of level-l cells around (cx, cy, cz): 27 independent loads
-__device__ __forceinline__ unsigned grid_box27(const GridDesc &g, const unsigned *__restrict__ base, int l, int cx, int cy, int cz) {
-    const unsigned *lv = base + g.off[l];
-    const int gx = g.dim[l][0], gy = g.dim[l][1], gz = g.dim[l][2];
-    unsigned v[27];
+    __shared__ unsigned sh[8];
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = cx + dx, y = cy + dy, z = cz + dz;
-                const bool in = (unsigned)x < (unsigned)gx && (unsigned)y < (unsigned)gy && (unsigned)z < (unsigned)gz;
-                v[(dz + 1) * 9 + (dy + 1) * 3 + dx + 1] = in ? __ldg(lv + ((size_t)z * gy + y) * gx + x) : 0u;
-            }
-    unsigned n = 0;
-#pragma unroll
-    for (int i = 0; i < 27; ++i) n += v[i];
-    return n;
-}
-
-// Upper bound of the k-th smallest reference-arithmetic distance from q to the cloud, or +inf (see the section header).
-// Tries the query's own level-0 cell, then the 3^3 box around it at levels 0, 1, 2, 3, 4, then the whole bounding box.
-__device__ __noinline__ float grid_tau0(const GridDesc &g, const unsigned *__restrict__ base, float qx, float qy, float qz, int k, float nq) {
-    if (!(isfinite(qx) && isfinite(qy) && isfinite(qz)) || g.n_finite < k) return CUDART_INF_F;
-    const float q[3] = {qx, qy, qz};
-    int c[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) c[a] = grid_cell(q[a], g.lo[a], g.inv_h, g.dim[0][a]);
-    int lev = -1, rho = 1;
-    {   // one round trip for most queries: own cell, level-0 box and level-1 box are requested together
-        const unsigned own = __ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]);
-        const unsigned n0 = grid_box27(g, base, 0, c[0], c[1], c[2]);
-        const unsigned n1 = grid_box27(g, base, 1, c[0] >> 1, c[1] >> 1, c[2] >> 1);
-        if (own >= (unsigned)k) { lev = 0; rho = 0; }
-        else if (n0 >= (unsigned)k) lev = 0;
-        else if (n1 >= (unsigned)k) lev = 1;
-        else
-            for (int l = 2; l < GRID_LEVELS; ++l)
-                if (grid_box27(g, base, l, c[0] >> l, c[1] >> l, c[2] >> l) >= (unsigned)k) { lev = l; break; }
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        (refs ? seg : qseg)[b * GRID_SEGS + blockIdx.x] = t;
     }
+}
+
+// counts -> start offsets (exclusive scan in the linear cell order): cend[c] = points in cells < c.  The scatter below then
+// advances cend[c] to the END of cell c (= start of cell c + 1).  z = 0: refs (counts -> cend), z = 1: queries (in place).
+__global__ void __launch_bounds__(256) grid_scan_kernel(const GridDesc *__restrict__ desc, const unsigned *__restrict__ counts,
+                                                        const unsigned *__restrict__ seg, unsigned *__restrict__ cend,
+                                                        unsigned *__restrict__ qcend, const unsigned *__restrict__ qseg) {
+    const int b = blockIdx.y, x = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool refs = blockIdx.z == 0;
+    const GridDesc &g = desc[b];
+    const int cells = g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
+    if (x * 1024 >= cells) return;
+    const unsigned *sg = (refs ? seg : qseg) + b * GRID_SEGS;
+    const unsigned *in = refs ? counts + (size_t)b * GRID_STRIDE : qcend + (size_t)b * GRID_MAX_CELLS;
+    unsigned *out = (refs ? cend : qcend) + (size_t)b * GRID_MAX_CELLS;
+    __shared__ unsigned sh[9];
+    if (warp == 0) {
+        unsigned v = 0;
+        for (int i = lane; i < x; i += 32) v += sg[i];
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (lane == 0) sh[8] = v;
+    }
+    const int c0 = x * 1024 + 4 * threadIdx.x;
+    uint4 v = *reinterpret_cast<const uint4 *>(in + c0);    // refs: may run into level 1, masked below
+    if (c0 + 0 >= cells) v.x = 0;
+    if (c0 + 1 >= cells) v.y = 0;
+    if (c0 + 2 >= cells) v.z = 0;
+    if (c0 + 3 >= cells) v.w = 0;
+    const unsigned mine = v.x + v.y + v.z + v.w;
+    unsigned inc = mine;                                   // inclusive scan over the warp, then over the 8 warps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    unsigned start = sh[8] + inc - mine;
+    for (int w = 0; w < warp; ++w) start += sh[w];
+    uint4 o4;
+    o4.x = start; o4.y = o4.x + v.x; o4.z = o4.y + v.y; o4.w = o4.z + v.z;
+    *reinterpret_cast<uint4 *>(out + c0) = o4;
+}
+
+// Move every point to its cell's range.  Refs: the sorted copy {x, y, z, index} for the seeds, the packed tile records of
+// the search (natural slot order = sorted order; layout as in pack_refs_kernel) and the slot -> index table; non-finite
+// refs go behind the finite ones, slots N .. n_pad-1 get padding records.  Queries: the sorted copy {x, y, z, index}.
+// The order inside a cell depends on the atomics; nothing downstream depends on it (seeds are functions of the SET of
+// refs in a box, the heap keys carry the caller's indices).
+// Tile slot of the ref at position p of the cell order: inside the ref range of one split (tps tiles) tile t takes the
+// positions t, t + tps, t + 2 tps, ... -- every tile is a uniform sample of the range, as in slot_to_ref, but a chunk of 8
+// slots now holds refs from a few neighbouring cells.  (Cutting the tiles straight from the cell order puts all the
+// candidates of a warp into 3-4 tiles: 60 % fewer drain iterations in the host simulation, tools/drain_sim.py, but
+// measured slower, 0.65 vs 0.56 ms -- the warps of a CTA share the tile ring and every heavy drain stalls the other 13;
+// and a query with a loose threshold sweeps towards its neighbourhood with every ref on the way beating the last: 2 ms.)
+__device__ __forceinline__ unsigned sorted_slot(unsigned p, int n_tiles, int tps) {
+    const unsigned span = (unsigned)tps * TILE, s = p / span, r = p - s * span;
+    const unsigned t = min((unsigned)tps, (unsigned)n_tiles - s * (unsigned)tps);      // tiles of this range
+    const unsigned q = r / t;
+    return s * span + (r - q * t) * TILE + q;
+}
+
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float *__restrict__ ref, int N, int n_pad, int tps, const float *__restrict__ qry,
+                                                           int S, const GridDesc *__restrict__ desc, GridBufs gb, float4 *__restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const GridDesc &g = desc[b];
+    if (i < n_pad) {
+        float x = CUDART_INF_F, y = 0.0f, z = 0.0f, w = CUDART_INF_F;    // padding (see pack_refs_kernel)
+        unsigned pos = (unsigned)i;
+        if (i < N) {
+            const float *r = ref + ((size_t)b * N + i) * 3;
+            x = r[0]; y = r[1]; z = r[2];
+            w = filter_norm(torch_sq_norm(x, y, z));
+            if (isfinite(x) && isfinite(y) && isfinite(z)) pos = atomicAdd(gb.cend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
+            else pos = (unsigned)g.n_finite + atomicAdd(gb.tail + b, 1u);
+            gb.sorted[(size_t)b * N + pos] = make_float4(x, y, z, __int_as_float(i));
+        }
+        const unsigned sl = sorted_slot(pos, n_pad / TILE, tps);
+        gb.perm[(size_t)b * n_pad + sl] = i;
+        const unsigned chunk = sl >> 3, slot = ((sl >> 1) & 3u) ^ (chunk & 3u);
+        float *o = reinterpret_cast<float *>(packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2) + (sl & 1u);
+        o[0] = x; o[2] = y; o[4] = z; o[6] = w;
+    } else if (i - n_pad < S) {
+        const int j = i - n_pad;
+        const float *qp = qry + ((size_t)b * S + j) * 3;
+        const float x = qp[0], y = qp[1], z = qp[2];
+        const unsigned pos = atomicAdd(gb.qcend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
+        gb.qsorted[(size_t)b * S + pos] = make_float4(x, y, z, __int_as_float(j));
+    }
+}
+
+// Corner bound: every ref of the box is closer than the box's farthest corner, so
+//   |q - farthest corner|^2 (1 + 1e-5) + 16 eps (|q|^2 + max|r|^2)
+// bounds the k-th smallest distance in the reference's rounding (lev < 0: the whole bounding box holds n_finite >= k refs).
+__device__ __forceinline__ float grid_corner_bound(const GridDesc &g, const float (&q)[3], const int (&c)[3], int lev, int rho, float nq) {
     float bound = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float L = g.lo[a], H = g.hi[a];                      // not found nearby: the whole bounding box holds n_finite >= k refs
+        float L = g.lo[a], H = g.hi[a];
         if (lev >= 0) {
             const int cl = c[a] >> lev, gl = g.dim[lev][a];
             const int c0 = cl - rho < 0 ? 0 : cl - rho, c1 = cl + rho >= gl ? gl - 1 : cl + rho;
@@ -319,6 +437,133 @@ __device__ __noinline__ float grid_tau0(const GridDesc &g, const unsigned *__res
         bound += m * m;
     }
     return bound * 1.00001f + (9.6e-7f * (nq + g.max_w) + 1e-37f);
+}
+
+// Starting threshold of every query: (an upper bound of) the k-th smallest distance to the refs INSIDE the first cell box
+// around the query that holds >= k refs (the cell itself, then the 3^3 box at levels 0..4), read from the cell-sorted copy.
+// Any k refs bound the k-th distance from above, whatever the geometry, so nothing here depends on how the cells were drawn.
+//   * ONE THREAD PER QUERY, queries in cell order: the threads of a warp sit in the same or neighbouring cells, so their
+//     box counts, row ranges and refs are the same addresses (one transaction per warp, L1 hits) and their loops have the
+//     same trip counts.  (Measured on the way: a thread per query in the CALLER's order 0.61 ms -- every thread chases its
+//     own chain of divergent loads; eight lanes per query with the rows flattened into one index range 0.14 ms --
+//     20 instructions of bookkeeping per ref.)
+//   * the k-th smallest is taken from a per-thread histogram in shared memory, 4 bins per octave of the squared distance,
+//     62 bins below the box's farthest corner: tau0 is the upper edge of the bin in which the count reaches k
+//     (<= 1.19 d_k); no ordered structure, no dependency between the refs (shared-memory REDs).
+//   * in the reference's rounding: the counted refs have |r|^2 <= 2|q|^2 + 2 d, the expanded forms are off by
+//     <= 10.03 eps (|q|^2 + |r|^2) <= 10.03 eps (3|q|^2 + 2 d) and this kernel's own fp32 evaluation by a few eps d,
+//     hence  tau0 = e (1 + 1e-5) + 16 eps (3|q|^2 + 2 e)  for the bin edge e.
+// Queries with no such box take the corner bound of the whole bounding box; non-finite queries and clouds with fewer than
+// k finite refs start from +inf.  Boxes of level >= `exact` are not looked into: their queries take the box's corner bound.
+constexpr int SEED_THREADS = 128, SEED_BINS = 64, SEED_SHIFT = 21, SEED_MAX_REFS = 192;
+__global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *__restrict__ qsorted, const float *__restrict__ qraw, int S, int N, int k,
+                                                                 const GridDesc *__restrict__ desc, const unsigned *__restrict__ counts,
+                                                                 const unsigned *__restrict__ cend, const float4 *__restrict__ sorted,
+                                                                 float *__restrict__ seed, int exact) {
+    __shared__ __align__(16) unsigned hist_all[SEED_BINS * SEED_THREADS];   // [bin][thread]
+    const int b = blockIdx.y, qi = blockIdx.x * SEED_THREADS + threadIdx.x;
+    {   // zero the histograms (16 bytes per store)
+        uint4 *hz = reinterpret_cast<uint4 *>(hist_all);
+        for (int i = threadIdx.x; i < SEED_BINS * SEED_THREADS / 4; i += SEED_THREADS) hz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    if (qi >= S) return;
+    float q[3];
+    if (qsorted) {
+        const float4 qv = __ldg(qsorted + (size_t)b * S + qi);
+        q[0] = qv.x; q[1] = qv.y; q[2] = qv.z;
+    } else {                                                   // the variant without sorting: queries in the caller's order
+        const float *qp = qraw + ((size_t)b * S + qi) * 3;
+        q[0] = __ldg(qp); q[1] = __ldg(qp + 1); q[2] = __ldg(qp + 2);
+    }
+    const GridDesc &g = desc[b];
+    float tau0 = CUDART_INF_F;
+    if (isfinite(q[0]) && isfinite(q[1]) && isfinite(q[2]) && g.n_finite >= k) {
+        const float nq = torch_sq_norm(q[0], q[1], q[2]);
+        const unsigned *base = counts + (size_t)b * GRID_STRIDE;
+        int c[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) c[a] = grid_cell(q[a], g.lo[a], g.inv_h, g.dim[0][a]);
+        // refs in the 3^3 box of level-l cells around the query: 27 independent loads
+        auto box27 = [&](int l) {
+            const int gx = g.dim[l][0], gy = g.dim[l][1], gz = g.dim[l][2];
+            const unsigned *lv = base + g.off[l];
+            const int cx = c[0] >> l, cy = c[1] >> l, cz = c[2] >> l;
+            unsigned n = 0;
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int x = cx + dx, y = cy + dy, z = cz + dz;
+                        const bool in = (unsigned)x < (unsigned)gx && (unsigned)y < (unsigned)gy && (unsigned)z < (unsigned)gz;
+                        n += in ? __ldg(lv + ((size_t)z * gy + y) * gx + x) : 0u;
+                    }
+            return n;
+        };
+        int lev = -1, rho = 1;
+        unsigned n_box = 0;
+        {
+            const unsigned own = __ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]);
+            if (own >= (unsigned)k) { lev = 0; rho = 0; n_box = own; }
+            else
+                for (int l = 0; l < GRID_LEVELS; ++l) {
+                    n_box = box27(l);
+                    if (n_box >= (unsigned)k) { lev = l; break; }
+                }
+        }
+        const float corner = grid_corner_bound(g, q, c, lev, rho, nq);
+        if (qsorted && lev >= 0 && lev < exact && corner < CUDART_INF_F) {
+            int lo0[3], hi0[3];                               // the box in level-0 cells
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int cl = c[a] >> lev, gla = g.dim[lev][a];
+                const int c0 = cl - rho < 0 ? 0 : cl - rho, c1 = cl + rho >= gla ? gla - 1 : cl + rho;
+                lo0[a] = c0 << lev;
+                hi0[a] = min(((c1 + 1) << lev) - 1, g.dim[0][a] - 1);
+            }
+            const int width = hi0[0] - lo0[0];
+            // bins: key = bits(d) >> 21 (8 exponent + 2 mantissa bits); the last bin but one holds the farthest corner, the last = overflow
+            const int base_key = max((int)(__float_as_uint(corner) >> SEED_SHIFT) - (SEED_BINS - 2), 0);
+            unsigned *hist = hist_all + threadIdx.x;
+            const unsigned *ce = cend + (size_t)b * GRID_MAX_CELLS;
+            const float4 *pts = sorted + (size_t)b * N;
+            auto count = [&](float4 r) {
+                const float dx = r.x - q[0], dy = r.y - q[1], dz = r.z - q[2];
+                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                int bin = (int)(__float_as_uint(d) >> SEED_SHIFT) - base_key;
+                bin = bin < 0 ? 0 : (bin > SEED_BINS - 1 ? SEED_BINS - 1 : bin);
+                atomicAdd(hist + bin * SEED_THREADS, 1u);       // result unused: a fire-and-forget RED, no read-modify-write chain
+            };
+            // A dense box is one long serial walk for its thread (1100 refs at C2: 40 us for a warp on its own, the whole
+            // kernel waits for it): look at every stride-th ref, ~SEED_MAX_REFS in all.  Any subset of the refs still
+            // bounds the k-th distance, only less tightly -- for the few queries at the edge of a dense region.
+            const unsigned stride = (n_box + SEED_MAX_REFS - 1) / SEED_MAX_REFS;
+            for (int z = lo0[2]; z <= hi0[2]; ++z)
+                for (int y = lo0[1]; y <= hi0[1]; ++y) {
+                    // the cells of one x-row are neighbours in the linear order: one contiguous range of sorted refs
+                    const int lin0 = (z * g.dim[0][1] + y) * g.dim[0][0] + lo0[0];
+                    unsigned p = lin0 > 0 ? __ldg(ce + lin0 - 1) : 0u;
+                    const unsigned end = __ldg(ce + lin0 + width);
+                    for (; p + 3 * stride < end; p += 4 * stride) {
+                        const float4 r0 = __ldg(pts + p), r1 = __ldg(pts + p + stride), r2 = __ldg(pts + p + 2 * stride), r3 = __ldg(pts + p + 3 * stride);
+                        count(r0); count(r1); count(r2); count(r3);
+                    }
+                    for (; p < end; p += stride) count(__ldg(pts + p));
+                }
+            unsigned cum = 0;
+            int bin = 0;
+            for (; bin < SEED_BINS; ++bin) {
+                cum += hist[bin * SEED_THREADS];
+                if (cum >= (unsigned)k) break;
+            }
+            const float e = __uint_as_float((unsigned)(base_key + bin + 1) << SEED_SHIFT);
+            if (bin < SEED_BINS - 1 && e < CUDART_INF_F) tau0 = e * 1.00001f + (9.6e-7f * (3.0f * nq + 2.0f * e) + 1e-37f);
+        }
+        tau0 = fminf(tau0, corner);
+    }
+    seed[(size_t)b * S + qi] = tau0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,8 +672,11 @@ struct SearchArgs {
     int debug_nodrain;     // measurement only: start with tau = -inf so nothing ever hits
     int lane_filter;       // 1: refs in registers, queries broadcast (default); 0: queries in registers, refs broadcast
     int n_split, tiles_per_split;
-    const GridDesc *grid;  // occupancy grid of the refs (one descriptor per batch item) or null: start from tau = +inf
-    const unsigned *counts;
+    // grid path (section 1b) or null: queries in cell order {x, y, z, index}, their starting thresholds, tile slot -> ref index
+    const float4 *qsorted; // [B][S]
+    const float *seed;     // [B][S]
+    const int *perm;       // [B][n_pad]
+    int interleave;        // cell-ordered queries dealt to the CTAs warp by warp (1) or in contiguous blocks (0)
     int64_t *idx_out;      // [B][S][k]   (n_split == 1)
     int32_t *idx32_out;    // same rows as 32-bit indices (host-buffer callers: halves the read-back); either may be null
     float *dist_out;       // [B][S][k] or null
@@ -559,25 +807,34 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
     __syncthreads();
 
     const int ct = threadIdx.x;  // 0 .. NCT-1
+    // Which query a thread owns.  Cell-ordered queries: contiguous blocks of the order by default (a CTA = a patch of space;
+    // measured 1-4 % faster on the lidar-like clouds), or dealt out warp by warp (B200PC_DRAIN=1: warp w of CTA x takes
+    // the (w * gridDim.x + x)-th group of 32, so that no CTA holds all the sparse, loosely bounded regions).
+    auto query_of = [&](int j) {
+        return P.qsorted && P.interleave ? (((j * NCW + (ct >> 5)) * (int)gridDim.x + (int)blockIdx.x) << 5) + lane : (int)blockIdx.x * QPB + j * NCT + ct;
+    };
     // Per-query state that stays in registers across the filter: tau (exact threshold) and the ball count.  Everything
     // else about a query is rebuilt from its 16-byte shared-memory record at the start of a drain.
     float tau[Q];
     int cnt[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-        const int qi = blockIdx.x * QPB + j * NCT + ct;
+        const int qi = query_of(j);
         float x = 0.f, y = 0.f, z = 0.f;
         if (qi < P.S) {
-            const float *qp = P.qry + ((size_t)b * P.S + qi) * 3;
-            x = qp[0]; y = qp[1]; z = qp[2];
+            if (P.qsorted) {
+                const float4 qv = __ldg(P.qsorted + (size_t)b * P.S + qi);
+                x = qv.x; y = qv.y; z = qv.z;
+            } else {
+                const float *qp = P.qry + ((size_t)b * P.S + qi) * 3;
+                x = qp[0]; y = qp[1]; z = qp[2];
+            }
         }
         cnt[j] = 0;
         if (MODE == MODE_TOPK) {
             tau[j] = P.debug_nodrain ? -CUDART_INF_F : CUDART_INF_F;
-            // warm start: a radius that provably holds >= k refs.  (Computed here rather than by a kernel of its own: that
-            // kernel took 16 us and this prologue got no shorter -- measured, profiles/r02_notes.md.)
-            if (P.grid && !P.debug_nodrain && qi < P.S)
-                tau[j] = grid_tau0(P.grid[b], P.counts + (size_t)b * GRID_STRIDE, x, y, z, k, torch_sq_norm(x, y, z));
+            // warm start: an upper bound of the k-th distance from grid_seed_kernel
+            if (P.seed && !P.debug_nodrain && qi < P.S) tau[j] = __ldg(P.seed + (size_t)b * P.S + qi);
             for (int e = 0; e < k; ++e) heap_all[e * QPB + j * NCT + ct] = HEAP_SENTINEL;
             heap_all[k * QPB + j * NCT + ct] = 0ull;   // pad: the smallest key, never selected as a child
         } else {
@@ -734,7 +991,8 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                                 if (d <= tau[j]) {
                                     // the refs are not visited in index order: an EQUAL distance still wins with a lower index
                                     // than the root's (rare; only then is the root read)
-                                    const uint32_t ri = (uint32_t)slot_to_ref(tile_ref0 + off, P.strided, P.n_pad / TILE);
+                                    const uint32_t ri = P.perm ? (uint32_t)__ldg(P.perm + (size_t)b * P.n_pad + tile_ref0 + off)
+                                                               : (uint32_t)slot_to_ref(tile_ref0 + off, P.strided, P.n_pad / TILE);
                                     if (d < tau[j] || ri < (uint32_t)lds_u64(hb)) {
                                         heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | ri);
                                         // never above the starting bound: the root is still the +inf sentinel until k refs are in
@@ -811,7 +1069,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
     // ---------------- results ----------------
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-        const int qi = blockIdx.x * QPB + j * NCT + ct;
+        const int qi = query_of(j);
         const int slot = j * NCT + ct;
         if (MODE == MODE_TOPK) {
             // in-place heapsort: ascending (distance, index) order
@@ -824,7 +1082,8 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
             }
         }
         if (qi >= P.S) continue;
-        const size_t row = (size_t)b * P.S + qi;
+        // cell-ordered queries: the result goes to the caller's row
+        const size_t row = (size_t)b * P.S + (P.qsorted ? __float_as_int(__ldg(&P.qsorted[(size_t)b * P.S + qi].w)) : qi);
         if (P.n_split == 1) {
             int64_t *io = P.idx_out ? P.idx_out + row * k : nullptr;
             int32_t *io32 = P.idx32_out ? P.idx32_out + row * k : nullptr;
@@ -951,12 +1210,16 @@ static const size_t kFixedSmem = (size_t)STAGES * TILE_BYTES + BAR_BYTES;
 // slots = SMs * CTAs-per-SM.  Among the candidates the one with the best wave efficiency wins;
 // ties go to more resident warps.
 // warm start only where it pays: the grid costs a memset, a bounding-box kernel and one atomic per ref
-static bool use_grid(int B, int N, int S, int k) {
+// 0: no grid; 1: counts + starting thresholds only (4 small launches); 2: refs and queries sorted by cell as well (7 launches)
+static int grid_mode(int B, int N, int S, int k) {
     const int g = tuning().grid;
-    if (g <= 0) return false;
-    if (g >= 2) return true;
-    // measured (tools/grid_probe.py): +6..16 % for k >= 3; a nearest-neighbour search (k = 1) inserts too little to pay for it
-    return k >= 3 && N >= 2048 && (long)B * N * S >= GRID_MIN_PAIRS;
+    if (g <= 0) return 0;
+    if (g == 2 || g == 3) return g - 1;                        // forced: 2 = thresholds only, 3 = sorted
+    // measured (tools/grid_probe.py): a nearest-neighbour search (k = 1) inserts too little to pay for any of it; the sorted
+    // variant wins where the drain is a large part of a long search (C2: -12 %, k = 64: -28 %) and loses its three extra
+    // launches on the short ones (fusion search of one frame pair, three-NN)
+    if (k < 3 || N < 2048 || (long)B * N * S < GRID_MIN_PAIRS) return 0;
+    return k >= 8 && (long)B * N * S >= GRID_SORT_MIN_PAIRS ? 2 : 1;
 }
 
 bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
@@ -1024,10 +1287,13 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
         const size_t rows = (size_t)B * S * pl->n_split;
         pl->part_bytes = align_up(rows * k * 4, 256) * (mode == MODE_TOPK ? 2 : 1) + align_up(rows * 4, 256);
     }
-    // occupancy grid for the warm start of a top-k search (section 1b): one descriptor + GRID_MAX_CELLS counters per batch item
+    // grid path of a top-k search (section 1b): counters, cell-sorted copies of refs and queries, one starting threshold per query
     pl->grid_bytes = 0;
-    if (mode == MODE_TOPK && use_grid(B, N, S, k))
-        pl->grid_bytes = align_up((size_t)B * sizeof(GridDesc), 256) + (size_t)B * GRID_STRIDE * sizeof(unsigned);
+    pl->grid_sorted = 0;
+    if (mode == MODE_TOPK && grid_mode(B, N, S, k)) {
+        pl->grid_bytes = grid_layout(B, N, S, pl->n_pad, nullptr, nullptr);
+        pl->grid_sorted = grid_mode(B, N, S, k) == 2;
+    }
     pl->total_bytes = pl->packed_bytes + pl->part_bytes + pl->grid_bytes;
     return true;
 }
@@ -1076,32 +1342,50 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     // (every prefix is a well-spread sample; measured 0.32 ms natural vs 0.36 ms strided on C3).
     const Tuning &tn = tuning();
     const int strided = mode == MODE_TOPK && (tn.natural_order >= 0 ? tn.natural_order == 0 : form != B200PC_FORM_QRY_NORM_FIRST);
-    GridDesc *gdesc = nullptr;
-    unsigned *gcounts = nullptr;
+    GridBufs gb{};
+    int strided_eff = strided;
     if (pl.grid_bytes) {
-        char *g = w + pl.packed_bytes + pl.part_bytes;
-        gdesc = reinterpret_cast<GridDesc *>(g);
-        gcounts = reinterpret_cast<unsigned *>(g + align_up((size_t)B * sizeof(GridDesc), 256));
-        B200PC_CUDA(cudaMemsetAsync(gcounts, 0, (size_t)B * GRID_STRIDE * sizeof(unsigned), st));
-        grid_bbox_kernel<<<B, 1024, 0, st>>>(ref, N, gdesc, gcounts);
+        grid_layout(B, N, S, pl.n_pad, w + pl.packed_bytes + pl.part_bytes, &gb);
+        const size_t zero_bytes = pl.grid_sorted ? reinterpret_cast<char *>(gb.cend) - reinterpret_cast<char *>(gb.counts)
+                                                 : (size_t)B * GRID_STRIDE * sizeof(unsigned);
+        B200PC_CUDA(cudaMemsetAsync(gb.counts, 0, zero_bytes, st));
+        grid_bbox_kernel<<<B, 1024, 0, st>>>(ref, N, gb.desc);
         B200PC_LAUNCH_CHECK();
     }
-    {
+    if (pl.grid_bytes && pl.grid_sorted) {
+        // count -> pyramid + segment sums -> scan -> scatter (sorted copies, packed tiles, slot table) -> starting thresholds
+        grid_count_kernel<<<dim3((N + S + 255) / 256, B), 256, 0, st>>>(ref, N, qry, S, gb.desc, gb.counts, gb.qcend);
+        B200PC_LAUNCH_CHECK();
+        grid_pyramid_kernel<<<dim3(GRID_SEGS, B, 2), 256, 0, st>>>(gb.desc, gb.counts, gb.seg, gb.qcend, gb.qseg);
+        B200PC_LAUNCH_CHECK();
+        grid_scan_kernel<<<dim3(GRID_SEGS, B, 2), 256, 0, st>>>(gb.desc, gb.counts, gb.seg, gb.cend, gb.qcend, gb.qseg);
+        B200PC_LAUNCH_CHECK();
+        grid_scatter_kernel<<<dim3((pl.n_pad + S + 255) / 256, B), 256, 0, st>>>(ref, N, pl.n_pad, pl.tiles_per_split, qry, S, gb.desc, gb, packed);
+        B200PC_LAUNCH_CHECK();
+        grid_seed_kernel<<<dim3((S + SEED_THREADS - 1) / SEED_THREADS, B), SEED_THREADS, 0, st>>>(gb.qsorted, nullptr, S, N, k, gb.desc, gb.counts, gb.cend,
+                                                                                            gb.sorted, gb.seed, tn.seed);
+        B200PC_LAUNCH_CHECK();
+        strided_eff = 0;                                  // the slot order is sorted_slot's
+    } else {
         dim3 grid((pl.n_pad / 2 + 255) / 256, B);
-        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, strided, packed, gdesc, gcounts);
+        pack_refs_kernel<<<grid, 256, 0, st>>>(ref, N, pl.n_pad, strided, packed, pl.grid_bytes ? gb.desc : nullptr, gb.counts);
         B200PC_LAUNCH_CHECK();
-    }
-    if (gdesc) {
-        grid_pyramid_kernel<<<dim3(128, B), 256, 0, st>>>(gdesc, gcounts);
-        B200PC_LAUNCH_CHECK();
+        if (pl.grid_bytes) {                              // thresholds only: the caller's order of refs and queries stays
+            grid_pyramid_kernel<<<dim3(GRID_SEGS, B, 1), 256, 0, st>>>(gb.desc, gb.counts, gb.seg, gb.qcend, gb.qseg);
+            B200PC_LAUNCH_CHECK();
+            grid_seed_kernel<<<dim3((S + SEED_THREADS - 1) / SEED_THREADS, B), SEED_THREADS, 0, st>>>(nullptr, qry, S, N, k, gb.desc, gb.counts, gb.cend,
+                                                                                                gb.sorted, gb.seed, 0);
+            B200PC_LAUNCH_CHECK();
+            gb.qsorted = nullptr; gb.perm = nullptr;
+        }
     }
 
     SearchArgs a;
-    a.packed = packed; a.strided = strided; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
+    a.packed = packed; a.strided = strided_eff; a.qry = qry; a.N = N; a.n_pad = pl.n_pad; a.S = S; a.k = k; a.r2 = r2;
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
     a.debug_nodrain = tn.nodrain;
     a.lane_filter = tn.filter >= 0 ? tn.filter != 0 : 1;                          // 0: A/B measurement only
-    a.grid = gdesc; a.counts = gcounts;
+    a.qsorted = gb.qsorted; a.seed = gb.seed; a.perm = gb.perm; a.interleave = tn.drain == 1;
     a.idx_out = idx; a.idx32_out = idx32; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;

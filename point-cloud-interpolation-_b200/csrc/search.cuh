@@ -19,7 +19,8 @@ struct SearchPlan {
     size_t smem_bytes;
     size_t packed_bytes;  // workspace: packed ref tiles
     size_t part_bytes;    // workspace: partial lists (n_split > 1)
-    size_t grid_bytes;    // workspace: occupancy grid (descriptors + counters) of a warm-started top-k search, else 0
+    size_t grid_bytes;    // workspace: occupancy grid (counters, sorted copies, starting thresholds) of a warm-started top-k search, else 0
+    int grid_sorted;      // 1: refs and queries are visited in cell order (search.cu section 1b)
     size_t total_bytes;
 };
 

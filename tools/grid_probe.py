@@ -1,5 +1,6 @@
-"""A/B of the occupancy-grid warm start of the top-k searches (B200PC_GRID=0 vs 1) on the bench shapes; checks that both
-return identical indices.  python tools/grid_probe.py"""
+"""A/B of the occupancy-grid variants of the top-k searches on the bench shapes: blind (B200PC_GRID=0), starting thresholds
+only (2), refs and queries visited in cell order as well (3; B200PC_DRAIN=1: contiguous instead of interleaved warps) and
+the default choice; checks that all return identical indices.  python tools/grid_probe.py"""
 import os
 import sys
 
@@ -28,14 +29,21 @@ def t(fn, n=10):
 def ab(name, fn, pairs):
     r = {}
     outs = {}
-    for g in ("0", "1"):
-        os.environ["B200PC_GRID"] = g; ops.reload_tuning()
-        outs[g] = fn()
-        r[g] = t(fn)
-    same = all(torch.equal(x, y) for x, y in zip(outs["0"], outs["1"])) if isinstance(outs["0"], tuple) else torch.equal(outs["0"], outs["1"])
-    print("%-52s blind %.3f ms (%.1f%%)  grid %.3f ms (%.1f%%)  identical=%s" % (
-        name, r["0"], pairs * 8 / r["0"] / 1e9 / 74.1 * 100, r["1"], pairs * 8 / r["1"] / 1e9 / 74.1 * 100, same), flush=True)
-    os.environ.pop("B200PC_GRID"); ops.reload_tuning()
+    modes = (("blind", "0", None, None), ("thresholds", "2", None, None), ("sorted", "3", None, None), ("sorted/contig", "3", None, "1"), ("default", None, None, None))
+    for m, g, sd, dr in modes:
+        for kk, v in (("B200PC_GRID", g), ("B200PC_SEED", sd), ("B200PC_DRAIN", dr)):
+            if v is None: os.environ.pop(kk, None)
+            else: os.environ[kk] = v
+        ops.reload_tuning()
+        outs[m] = fn()
+        r[m] = t(fn)
+    def eq(x, y):
+        return all(torch.equal(u, v) for u, v in zip(x, y)) if isinstance(x, tuple) else torch.equal(x, y)
+    same = all(eq(outs["blind"], outs[m[0]]) for m in modes[1:])
+    print("%-46s " % name + "  ".join("%s %.3f (%.1f%%)" % (m[0], r[m[0]], pairs * 8 / r[m[0]] / 1e9 / 74.1 * 100) for m in modes)
+          + "  identical=%s" % same, flush=True)
+    for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_DRAIN"): os.environ.pop(kk, None)
+    ops.reload_tuning()
 
 
 a, b = synth.batch_pairs(0, 8, 16384)
