@@ -13,7 +13,7 @@
 //      never be selected; the 4 pairs of an 8-ref chunk are XOR-swizzled by the chunk number so that
 //      lanes re-visiting different chunks spread over the banks.  For top-k searches tile t holds refs t, t + n_tiles, ...
 //      (slot_to_ref): a strided sample of the cloud per tile, whatever order the caller's points are in.
-//   2. search_kernel: 8 KB tiles stream through a 3-stage shared-memory ring (cp.async.bulk + mbarrier;
+//   2. search_kernel: 8 KB tiles stream through a 4-stage shared-memory ring (cp.async.bulk + mbarrier;
 //      no producer warp: the warp that releases a stage last refills it).  Every thread OWNS Q queries:
 //      their k-best heap lives in shared memory and their threshold tau in a register.
 //   3. FILTER.  The prefilter value of a (query, ref) pair is
@@ -44,7 +44,7 @@ namespace b200pc {
 
 constexpr int TILE = 512;                  // refs per shared-memory tile
 constexpr int TILE_BYTES = TILE * 16;      // 8 KB
-constexpr int STAGES = 3;                  // ring depth
+constexpr int STAGES = 4;                  // ring depth (3 -> 4 with an 8-entry candidate buffer: -3 % at C2 once the queries are cell-ordered)
 constexpr int CHUNK = 8;                   // refs per threshold test
 constexpr int REC = 8;                     // 16-byte records per chunk
 constexpr int CHUNKS_PER_TILE = TILE / CHUNK;
@@ -728,7 +728,7 @@ __device__ __forceinline__ void heap_sift_root(uint32_t hb, uint32_t SB, uint32_
     sts_u64(hb + pos, nk);
 }
 
-constexpr int CAND_CAP = 16;  // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a drain pass
+constexpr int CAND_CAP = 8;   // per-query buffer: one u16 entry (chunk << 8 | candidate mask) per hit chunk of a drain pass
 
 // Exact distance of ONE ref of the tile (ref number `off`), scalar: the same IEEE operations in the same order as
 // pair_dist (explicit .rn intrinsics, so nothing is contracted), a third of its instructions.  (ax, ay, az) is -2q for

@@ -1,5 +1,5 @@
 """A/B of the occupancy-grid variants of the top-k searches on the bench shapes: blind (B200PC_GRID=0), starting thresholds
-only (2), refs and queries visited in cell order as well (3; B200PC_DRAIN=1: contiguous instead of interleaved warps) and
+only (2), refs and queries visited in cell order as well (3; B200PC_DRAIN=1: warps dealt out over the CTAs instead of contiguous blocks) and
 the default choice; checks that all return identical indices.  python tools/grid_probe.py"""
 import os
 import sys
@@ -29,7 +29,7 @@ def t(fn, n=10):
 def ab(name, fn, pairs):
     r = {}
     outs = {}
-    modes = (("blind", "0", None, None), ("thresholds", "2", None, None), ("sorted", "3", None, None), ("sorted/contig", "3", None, "1"), ("default", None, None, None))
+    modes = (("blind", "0", None, None), ("thresholds", "2", None, None), ("sorted", "3", None, None), ("sorted/interleaved", "3", None, "1"), ("default", None, None, None))
     for m, g, sd, dr in modes:
         for kk, v in (("B200PC_GRID", g), ("B200PC_SEED", sd), ("B200PC_DRAIN", dr)):
             if v is None: os.environ.pop(kk, None)
