@@ -722,7 +722,7 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (search_kernel): FP32 CUDA-core pipe -----------------
-    per_launch_s = secs / args.steps                       # pack_refs (~2 us) + search kernel, this rank
+    per_launch_s = secs / args.steps                       # the whole knn_point call: grid / sort kernels (~50 us) + search kernel, this rank
     pairs = BATCH * NPTS * NPTS
     achieved = pairs * FLOP_PER_PAIR / per_launch_s / 1e12
     try:
@@ -732,17 +732,18 @@ def main():
     peak = fma_tf if fma_tf else FP32_NOMINAL_TFLOPS
     roofline = {"bound": "fp32_cuda_core", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of search_kernel from one `ncu --set full` capture of this very
-                # call (profiles/r02_ncu_knn.txt: 5.26 MB read = the packed refs and the grid counters once, 0 written: the 16.8 MB
-                # of indices stay in L2 until evicted); a counter, so a constant from the committed capture, not measured live
-                "traffic": 5255680, "traffic_source": "profiles/r02_ncu_knn.txt (ncu --set full, same shape)",
+                # call (profiles/r02_ncu_knn.txt: 5.28 MB read = the packed refs, sorted queries and thresholds once, 14 KB written:
+                # the 16.8 MB of indices stay in L2 until evicted); a counter, so a constant from the committed capture, not measured live
+                "traffic": 5290496, "traffic_source": "profiles/r02_ncu_knn.txt (ncu --set full, same shape)",
                 "peak_source": "b200pc_fma_peak FFMA2 micro-kernel measured in this run (MEASURED_PEAKS.json has no FP32 entry)"
                 if fma_tf else "nominal",
                 "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_nominal": achieved / FP32_NOMINAL_TFLOPS,
                 "algorithmic": "8 FLOP per (query, ref) pair x %d pairs per launch" % pairs,
                 "note": "K=3 contraction on FP32 CUDA cores (tensor cores would break the rounding parity); the "
                         "contract's enum is hbm|tensor, this kernel is neither: ncu shows it bound by instruction issue (lane "
-                        "filter 40 %, lock-step heap drain 45 % of 428 M warp instructions, profiles/r02_notes.md), DRAM "
-                        "traffic is 5.3 MB against 17.2 GFLOP"}
+                        "filter 49 %, lock-step heap drain 29 % of 359 M warp instructions, profiles/r02_notes.md), DRAM "
+                        "traffic is 5.3 MB against 17.2 GFLOP.  `achieved` divides by the whole call (6 grid / sort kernels "
+                        "+ the search kernel), not by the search kernel alone"}
 
     # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
     cval, csec, cthreads, ckind = cpu_reference_knn(a, b, reps=3)
@@ -762,9 +763,9 @@ def main():
                     "int64_value": queries_per_step / e2e_res["pipelined"] / 1e9, "int64_d2h_bytes_per_step": d2h_bytes,
                     "serial_int64_value": queries_per_step / e2e_res["serial"] / 1e9,
                     "numa_cpulist": numa},
-            # per knn_point call at C2 (no ref split): grid_bbox_kernel, pack_refs_kernel, grid_pyramid_kernel, search_kernel
-            # (+ one memset node for the grid counters); timed steps only
-            "gpu_launches": int(args.steps * 4), "abi_calls_incl_warmup": int(abi_calls),
+            # per knn_point call at C2 (no ref split): grid_bbox, grid_count, grid_pyramid, grid_scan, grid_scatter, grid_seed and
+            # search_kernel (+ one memset node for the grid counters); timed steps only
+            "gpu_launches": int(args.steps * 7), "abi_calls_incl_warmup": int(abi_calls),
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     if pn:
         line["pointinet"] = {"metric": "pointinet_interp_frames_per_s", "workload": "C1: PointINet forward, 16384 points, batch 1 per GPU, t=0.5, random weights",

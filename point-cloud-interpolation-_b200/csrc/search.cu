@@ -34,6 +34,9 @@
 //      (distance, index): ties go to the lower index whatever the visiting order.
 //   5. When there are too few queries to fill 148 SMs the ref range is split over gridDim.z and
 //      a small merge kernel combines the partial lists.
+//   6. Top-k searches with k >= 3 that are large enough go through an occupancy grid of the refs (section 1b): every
+//      query starts from a threshold that provably holds k refs, and the long searches (C2) also visit refs and queries
+//      in cell order -- same pairs, same keys, bit-identical results, a third fewer instructions.
 #include "search.cuh"
 
 #include <math.h>
