@@ -376,6 +376,79 @@ __global__ void __launch_bounds__(256) grid_scan_kernel(const GridDesc *__restri
 // refs go behind the finite ones, slots N .. n_pad-1 get padding records.  Queries: the sorted copy {x, y, z, index}.
 // The order inside a cell depends on the atomics; nothing downstream depends on it (seeds are functions of the SET of
 // refs in a box, the heap keys carry the caller's indices).
+// Corner bound: every ref of the box is closer than the box's farthest corner, so
+//   |q - farthest corner|^2 (1 + 1e-5) + 16 eps (|q|^2 + max|r|^2)
+// bounds the k-th smallest distance in the reference's rounding (lev < 0: the whole bounding box holds n_finite >= k refs).
+__device__ __forceinline__ float grid_corner_bound(const GridDesc &g, const float (&q)[3], const int (&c)[3], int lev, int rho, float nq) {
+    float bound = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float L = g.lo[a], H = g.hi[a];
+        if (lev >= 0) {
+            const int cl = c[a] >> lev, gl = g.dim[lev][a];
+            const int c0 = cl - rho < 0 ? 0 : cl - rho, c1 = cl + rho >= gl ? gl - 1 : cl + rho;
+            const float hl = g.h * (float)(1 << lev);
+            L = g.lo[a] + (float)c0 * hl;
+            const float Hn = g.lo[a] + (float)(c1 + 1) * hl;  // the last cell also takes the refs clamped into it
+            H = c1 == gl - 1 ? fmaxf(Hn, g.hi[a]) : Hn;
+        }
+        // a ref counted in cell c lies in [lo + c h, lo + (c+1) h] up to the rounding of (v - lo) * inv_h: widen by delta
+        const float delta = 1e-3f * g.h + 1e-6f * fmaxf(fabsf(g.lo[a]), fabsf(g.hi[a]));
+        const float m = fmaxf(fabsf(q[a] - (L - delta)), fabsf((H + delta) - q[a]));
+        bound += m * m;
+    }
+    return bound * 1.00001f + (9.6e-7f * (nq + g.max_w) + 1e-37f);
+}
+
+// refs counted in the 3 x 3 x 3 box of level-l cells around level-0 cell c: 27 independent loads
+__device__ __forceinline__ unsigned grid_box27(const GridDesc &g, const unsigned *__restrict__ base, const int (&c)[3], int l) {
+    const int gx = g.dim[l][0], gy = g.dim[l][1], gz = g.dim[l][2];
+    const unsigned *lv = base + g.off[l];
+    const int cx = c[0] >> l, cy = c[1] >> l, cz = c[2] >> l;
+    unsigned n = 0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                const bool in = (unsigned)x < (unsigned)gx && (unsigned)y < (unsigned)gy && (unsigned)z < (unsigned)gz;
+                n += in ? __ldg(lv + ((size_t)z * gy + y) * gx + x) : 0u;
+            }
+    return n;
+}
+
+// The first cell box around the query's level-0 cell c that holds >= k refs: the cell itself (lev 0, rho 0), then the 3^3 box
+// at levels 0..4 (rho 1); lev = -1 if none does.  n_box = the refs it holds.
+__device__ __forceinline__ void grid_find_box(const GridDesc &g, const unsigned *__restrict__ base, const int (&c)[3], int k, int &lev, int &rho,
+                                              unsigned &n_box) {
+    lev = -1; rho = 1; n_box = 0;
+    // one round trip for most queries: own cell, level-0 box and level-1 box are requested together
+    const unsigned own = __ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]);
+    const unsigned n0 = grid_box27(g, base, c, 0), n1 = grid_box27(g, base, c, 1);
+    if (own >= (unsigned)k) { lev = 0; rho = 0; n_box = own; }
+    else if (n0 >= (unsigned)k) { lev = 0; n_box = n0; }
+    else if (n1 >= (unsigned)k) { lev = 1; n_box = n1; }
+    else
+        for (int l = 2; l < GRID_LEVELS; ++l) {
+            n_box = grid_box27(g, base, c, l);
+            if (n_box >= (unsigned)k) { lev = l; break; }
+        }
+}
+
+// Starting threshold of one query from the counts alone: the corner bound of its box, +inf for a non-finite query or a cloud
+// with fewer than k finite refs.
+__device__ __forceinline__ float grid_corner_seed(const GridDesc &g, const unsigned *__restrict__ base, const float (&q)[3], int k) {
+    if (!(isfinite(q[0]) && isfinite(q[1]) && isfinite(q[2])) || g.n_finite < k) return CUDART_INF_F;
+    int c[3], lev, rho;
+    unsigned n_box;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[a] = grid_cell(q[a], g.lo[a], g.inv_h, g.dim[0][a]);
+    grid_find_box(g, base, c, k, lev, rho, n_box);
+    return grid_corner_bound(g, q, c, lev, rho, torch_sq_norm(q[0], q[1], q[2]));
+}
+
 // Tile slot of the ref at position p of the cell order: inside the ref range of one split (tps tiles) tile t takes the
 // positions t, t + tps, t + 2 tps, ... -- every tile is a uniform sample of the range, as in slot_to_ref, but a chunk of 8
 // slots now holds refs from a few neighbouring cells.  (Cutting the tiles straight from the cell order puts all the
@@ -390,7 +463,7 @@ __device__ __forceinline__ unsigned sorted_slot(unsigned p, int n_tiles, int tps
 }
 
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const float *__restrict__ ref, int N, int n_pad, int tps, const float *__restrict__ qry,
-                                                           int S, const GridDesc *__restrict__ desc, GridBufs gb, float4 *__restrict__ packed) {
+                                                           int S, const GridDesc *__restrict__ desc, GridBufs gb, float4 *__restrict__ packed, int k_seed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     const GridDesc &g = desc[b];
     if (i < n_pad) {
@@ -415,31 +488,11 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float *__restri
         const float x = qp[0], y = qp[1], z = qp[2];
         const unsigned pos = atomicAdd(gb.qcend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
         gb.qsorted[(size_t)b * S + pos] = make_float4(x, y, z, __int_as_float(j));
-    }
-}
-
-// Corner bound: every ref of the box is closer than the box's farthest corner, so
-//   |q - farthest corner|^2 (1 + 1e-5) + 16 eps (|q|^2 + max|r|^2)
-// bounds the k-th smallest distance in the reference's rounding (lev < 0: the whole bounding box holds n_finite >= k refs).
-__device__ __forceinline__ float grid_corner_bound(const GridDesc &g, const float (&q)[3], const int (&c)[3], int lev, int rho, float nq) {
-    float bound = 0.0f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float L = g.lo[a], H = g.hi[a];
-        if (lev >= 0) {
-            const int cl = c[a] >> lev, gl = g.dim[lev][a];
-            const int c0 = cl - rho < 0 ? 0 : cl - rho, c1 = cl + rho >= gl ? gl - 1 : cl + rho;
-            const float hl = g.h * (float)(1 << lev);
-            L = g.lo[a] + (float)c0 * hl;
-            const float Hn = g.lo[a] + (float)(c1 + 1) * hl;  // the last cell also takes the refs clamped into it
-            H = c1 == gl - 1 ? fmaxf(Hn, g.hi[a]) : Hn;
+        if (k_seed > 0) {                                  // the query's starting threshold, here rather than in a launch of its own
+            const float q[3] = {x, y, z};
+            gb.seed[(size_t)b * S + pos] = grid_corner_seed(g, gb.counts + (size_t)b * GRID_STRIDE, q, k_seed);
         }
-        // a ref counted in cell c lies in [lo + c h, lo + (c+1) h] up to the rounding of (v - lo) * inv_h: widen by delta
-        const float delta = 1e-3f * g.h + 1e-6f * fmaxf(fabsf(g.lo[a]), fabsf(g.hi[a]));
-        const float m = fmaxf(fabsf(q[a] - (L - delta)), fabsf((H + delta) - q[a]));
-        bound += m * m;
     }
-    return bound * 1.00001f + (9.6e-7f * (nq + g.max_w) + 1e-37f);
 }
 
 // Starting threshold of every query: (an upper bound of) the k-th smallest distance to the refs INSIDE the first cell box
@@ -487,35 +540,9 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
         int c[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) c[a] = grid_cell(q[a], g.lo[a], g.inv_h, g.dim[0][a]);
-        // refs in the 3^3 box of level-l cells around the query: 27 independent loads
-        auto box27 = [&](int l) {
-            const int gx = g.dim[l][0], gy = g.dim[l][1], gz = g.dim[l][2];
-            const unsigned *lv = base + g.off[l];
-            const int cx = c[0] >> l, cy = c[1] >> l, cz = c[2] >> l;
-            unsigned n = 0;
-#pragma unroll
-            for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int x = cx + dx, y = cy + dy, z = cz + dz;
-                        const bool in = (unsigned)x < (unsigned)gx && (unsigned)y < (unsigned)gy && (unsigned)z < (unsigned)gz;
-                        n += in ? __ldg(lv + ((size_t)z * gy + y) * gx + x) : 0u;
-                    }
-            return n;
-        };
-        int lev = -1, rho = 1;
-        unsigned n_box = 0;
-        {
-            const unsigned own = __ldg(base + ((size_t)c[2] * g.dim[0][1] + c[1]) * g.dim[0][0] + c[0]);
-            if (own >= (unsigned)k) { lev = 0; rho = 0; n_box = own; }
-            else
-                for (int l = 0; l < GRID_LEVELS; ++l) {
-                    n_box = box27(l);
-                    if (n_box >= (unsigned)k) { lev = l; break; }
-                }
-        }
+        int lev, rho;
+        unsigned n_box;
+        grid_find_box(g, base, c, k, lev, rho, n_box);
         const float corner = grid_corner_bound(g, q, c, lev, rho, nq);
         if (qsorted && lev >= 0 && lev < exact && corner < CUDART_INF_F) {
             int lo0[3], hi0[3];                               // the box in level-0 cells
@@ -1363,11 +1390,14 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
         B200PC_LAUNCH_CHECK();
         grid_scan_kernel<<<dim3(GRID_SEGS, B, 2), 256, 0, st>>>(gb.desc, gb.counts, gb.seg, gb.cend, gb.qcend, gb.qseg);
         B200PC_LAUNCH_CHECK();
-        grid_scatter_kernel<<<dim3((pl.n_pad + S + 255) / 256, B), 256, 0, st>>>(ref, N, pl.n_pad, pl.tiles_per_split, qry, S, gb.desc, gb, packed);
+        grid_scatter_kernel<<<dim3((pl.n_pad + S + 255) / 256, B), 256, 0, st>>>(ref, N, pl.n_pad, pl.tiles_per_split, qry, S, gb.desc, gb, packed,
+                                                                                  tn.seed > 0 ? 0 : k);
         B200PC_LAUNCH_CHECK();
-        grid_seed_kernel<<<dim3((S + SEED_THREADS - 1) / SEED_THREADS, B), SEED_THREADS, 0, st>>>(gb.qsorted, nullptr, S, N, k, gb.desc, gb.counts, gb.cend,
-                                                                                            gb.sorted, gb.seed, tn.seed);
-        B200PC_LAUNCH_CHECK();
+        if (tn.seed > 0) {                               // thresholds from the refs inside the boxes (A/B: B200PC_SEED=n); else the scatter wrote them
+            grid_seed_kernel<<<dim3((S + SEED_THREADS - 1) / SEED_THREADS, B), SEED_THREADS, 0, st>>>(gb.qsorted, nullptr, S, N, k, gb.desc, gb.counts,
+                                                                                                gb.cend, gb.sorted, gb.seed, tn.seed);
+            B200PC_LAUNCH_CHECK();
+        }
         strided_eff = 0;                                  // the slot order is sorted_slot's
     } else {
         dim3 grid((pl.n_pad / 2 + 255) / 256, B);
