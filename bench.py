@@ -742,7 +742,7 @@ def main():
                 "note": "K=3 contraction on FP32 CUDA cores (tensor cores would break the rounding parity); the "
                         "contract's enum is hbm|tensor, this kernel is neither: ncu shows it bound by instruction issue (lane "
                         "filter 49 %, lock-step heap drain 29 % of 359 M warp instructions, profiles/r02_notes.md), DRAM "
-                        "traffic is 5.3 MB against 17.2 GFLOP.  `achieved` divides by the whole call (6 grid / sort kernels "
+                        "traffic is 5.3 MB against 17.2 GFLOP.  `achieved` divides by the whole call (5 grid / sort kernels "
                         "+ the search kernel), not by the search kernel alone"}
 
     # ---- CPU baseline beside it (bounded sample: one of the 8 pairs) --------------------------
@@ -763,9 +763,9 @@ def main():
                     "int64_value": queries_per_step / e2e_res["pipelined"] / 1e9, "int64_d2h_bytes_per_step": d2h_bytes,
                     "serial_int64_value": queries_per_step / e2e_res["serial"] / 1e9,
                     "numa_cpulist": numa},
-            # per knn_point call at C2 (no ref split): grid_bbox, grid_count, grid_pyramid, grid_scan, grid_scatter, grid_seed and
-            # search_kernel (+ one memset node for the grid counters); timed steps only
-            "gpu_launches": int(args.steps * 7), "abi_calls_incl_warmup": int(abi_calls),
+            # per knn_point call at C2 (no ref split): grid_bbox, grid_count, grid_pyramid, grid_scan, grid_scatter (which also writes the
+            # starting thresholds) and search_kernel (+ one memset node for the grid counters); timed steps only
+            "gpu_launches": int(args.steps * 6), "abi_calls_incl_warmup": int(abi_calls),
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     if pn:
         line["pointinet"] = {"metric": "pointinet_interp_frames_per_s", "workload": "C1: PointINet forward, 16384 points, batch 1 per GPU, t=0.5, random weights",
