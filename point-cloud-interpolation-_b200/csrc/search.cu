@@ -116,13 +116,13 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
 // A streaming k-best that starts from tau = +inf pays k(1 + ln(N/k)) heap inserts per query (127 at C2), more than half of
 // them in the first tile, and in lock-step a warp pays the maximum over its lanes (profiles/r01_notes.md: the drain is
 // 50 % of the kernel).  Nothing forces the search to start blind, or to visit the points in the caller's order:
-//   * the refs are counted into a uniform grid over their bounding box (<= 128 cells along the longest axis, <= 131072
-//     cells) with a pyramid of four coarser levels, and SORTED by cell (counting sort: count, scan, scatter).  The tiles of
-//     the search are cut from the sorted order, so the refs near a query sit in a handful of tiles;
-//   * the queries are sorted by the cell of the same grid they fall into, so the 32 queries of a warp are neighbours in
-//     space: their candidates come in the same few tiles and in similar numbers (the lock-step drain stops idling);
-//   * every query starts from tau0 = (an upper bound of) the k-th smallest distance to the refs of the first cell box
-//     around it that holds >= k refs (grid_seed_kernel).
+//   * THRESHOLDS (every gridded search, grid_mode >= 1).  The refs are counted into a uniform grid over their bounding box
+//     (<= 128 cells along the longest axis, <= 131072 cells) with a pyramid of four coarser levels; a query starts from
+//     tau0 = squared distance to the farthest corner of the first cell box around it (its cell, the 3^3 box at levels
+//     0..4, else the bounding box) that holds >= k refs, inflated by the rounding error of the reference's expanded forms.
+//   * CELL ORDER (the long searches, grid_mode 2).  Refs and queries are counting-sorted by cell (count, scan, scatter).
+//     The 32 queries of a warp are then neighbours in space: their candidates come in the same chunks and in similar
+//     numbers, so the lock-step drain idles less.  The tiles are a strided sample of the sorted refs (sorted_slot).
 // Every (query, ref) pair still goes through the filter -- this is brute force in a different visiting order with a warm
 // start; tau0 is only ever an upper bound and the heap's (distance, index) keys do not depend on the visiting order, so the
 // results are bit-identical.  Outputs are written to the rows of the caller's query order.
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float *__restri
             w = filter_norm(torch_sq_norm(x, y, z));
             if (isfinite(x) && isfinite(y) && isfinite(z)) pos = atomicAdd(gb.cend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
             else pos = (unsigned)g.n_finite + atomicAdd(gb.tail + b, 1u);
-            gb.sorted[(size_t)b * N + pos] = make_float4(x, y, z, __int_as_float(i));
+            if (k_seed == 0) gb.sorted[(size_t)b * N + pos] = make_float4(x, y, z, __int_as_float(i));   // only grid_seed_kernel reads it
         }
         const unsigned sl = sorted_slot(pos, n_pad / TILE, tps);
         gb.perm[(size_t)b * n_pad + sl] = i;
@@ -1068,6 +1068,14 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         // the warm-up schedule of the first tile is only needed by warps that hold a query starting from tau = +inf
         const bool warm = MODE == MODE_TOPK && t == 0 && warp_cold;
         int c = 0;
+        if (MODE == MODE_BALL) {
+            // a ball is "the first nsample refs by index": once every query of the warp has its nsample refs, no later ref
+            // can change anything -- the warp only keeps releasing stages so that the other warps' tiles keep coming
+            bool full = true;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) full = full && cnt[j] == k;
+            if (__all_sync(FULL, full)) c = CHUNKS_PER_TILE;
+        }
         while (c < CHUNKS_PER_TILE) {
             int nch = CHUNKS_PER_TILE - c;
             if (P.lane_filter && !(warm && c < 32)) {
