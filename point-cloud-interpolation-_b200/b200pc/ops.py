@@ -61,6 +61,13 @@ def _workspace(nbytes, dev):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
 
 
+def _search_ws(lib, B, N, S, k):
+    """workspace of a search call; sized under the SAME tuning state the call itself will see"""
+    if TUNING_AUTORELOAD:
+        lib.b200pc_tuning_reload()
+    return lib.b200pc_search_workspace_bytes(B, N, S, k)
+
+
 def _call(dev, fn, *args):
     """one C-ABI compute call on `dev` (current stream), error code -> exception"""
     global launch_count
@@ -147,7 +154,7 @@ def _knn(ref, qry, k, form, want_dist):
     idx = _i64(B, S, k, like=ref)
     dist = _f32(B, S, k, like=ref) if want_dist else None
     lib = _lib.load()
-    nws = lib.b200pc_search_workspace_bytes(B, N, S, k)
+    nws = _search_ws(lib, B, N, S, k)
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_knn, _ptr(ref), _ptr(qry), B, N, S, k, int(form), _ptr(idx), _ptr(dist), _ptr(ws), nws, _stream(dev))
     return idx, (dist if want_dist else _f32(B, S, 0, like=ref))
@@ -159,7 +166,7 @@ def _knn_i32(ref, qry, k, form):
     dev = ref.device
     idx = torch.empty(B, S, k, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    nws = lib.b200pc_search_workspace_bytes(B, N, S, k)
+    nws = _search_ws(lib, B, N, S, k)
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_knn_i32, _ptr(ref), _ptr(qry), B, N, S, k, int(form), _ptr(idx), C.c_void_p(0), _ptr(ws), nws, _stream(dev))
     return idx
@@ -172,7 +179,7 @@ def _ball_query(xyz, new_xyz, r2, nsample):
     dev = xyz.device
     idx = _i64(B, S, nsample, like=xyz)
     lib = _lib.load()
-    nws = lib.b200pc_search_workspace_bytes(B, N, S, nsample)
+    nws = _search_ws(lib, B, N, S, nsample)
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_ball_query, _ptr(xyz), _ptr(new_xyz), B, N, S, C.c_float(r2), nsample, _ptr(idx), _ptr(ws), nws, _stream(dev))
     return idx
@@ -306,7 +313,7 @@ def _three_nn(unknown, known, variant, want_weight):
     idx = _i64(B, N, 3, like=unknown)
     weight = _f32(B, N, 3, like=unknown) if want_weight else None
     lib = _lib.load()
-    nws = lib.b200pc_search_workspace_bytes(B, S, N, 3)
+    nws = _search_ws(lib, B, S, N, 3)
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_three_nn, _ptr(unknown), _ptr(known), B, N, S, int(variant), _ptr(dist), _ptr(idx), _ptr(weight), _ptr(ws),
           nws, _stream(dev))
@@ -405,7 +412,7 @@ def _fusion_group(qry, ref, feat, k):
     gf = _f32(B, Cf, S, k, like=qry)
     idx = _i64(B, S, k, like=qry)
     lib = _lib.load()
-    nws = lib.b200pc_search_workspace_bytes(B, N, S, k)
+    nws = _search_ws(lib, B, N, S, k)
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_fusion_group, _ptr(qry), _ptr(ref), _ptr(feat if Cf else None), B, N, S, k, Cf, _ptr(resi), _ptr(nn),
           _ptr(gf if Cf else None), _ptr(idx), _ptr(ws), nws, _stream(dev))
@@ -451,7 +458,7 @@ def _chamfer_fwd(x, y):
     dy = _f32(B, M, like=x); iy = _i64(B, M, like=x)
     loss = _f32((), like=x)
     lib = _lib.load()
-    nws = max(lib.b200pc_search_workspace_bytes(B, M, N, 1), lib.b200pc_search_workspace_bytes(B, N, M, 1))
+    nws = max(_search_ws(lib, B, M, N, 1), _search_ws(lib, B, N, M, 1))
     ws = _workspace(nws, dev)
     _call(dev, lib.b200pc_chamfer_fwd, _ptr(x), _ptr(y), B, N, M, _ptr(dx), _ptr(ix), _ptr(dy), _ptr(iy), _ptr(loss), _ptr(ws), nws,
           _stream(dev))
