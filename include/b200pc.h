@@ -53,7 +53,9 @@ void b200pc_tuning_reload(void);
 
 /* ---- scratch sizing -------------------------------------------------------------------- */
 /* scratch for any neighbour search (knn / ball_query / three_nn / chamfer) of S queries
- * against N refs per batch item with lists of length k (k = nsample for the ball query). */
+ * against N refs per batch item with lists of length k (k = nsample for the ball query): the packed reference
+ * records, the partial lists of a split search and, for the large top-k searches, the occupancy grid with the
+ * cell-ordered copies of references and queries (csrc/search.cu section 1b; ~1.8 MB per batch item). */
 size_t b200pc_search_workspace_bytes(int B, int N, int S, int k);
 /* FPS keeps a cloud in the registers of one thread-block cluster and needs NO scratch: this query returns a token 256 and
  * b200pc_fps ignores its workspace arguments (both kept so that every compute entry has the same calling shape). */
