@@ -303,6 +303,99 @@ def test_filter_threshold_is_conservative_for_all_three_forms(scale, offset):
         assert (u < thr).all(), "form %d: %d of %d pairs would be filtered out" % (form, int((~(u < thr)).sum()), n)
 
 
+# ---------------------------------------------------------------- the occupancy grid of the top-k searches, emulated
+def _sorted_slot(p, n_tiles, tps, TILE=512):
+    """search.cu sorted_slot(): tile slot of the ref at position p of the cell order"""
+    span = tps * TILE
+    s = p // span
+    r = p - s * span
+    t = np.minimum(tps, n_tiles - s * tps)
+    q = r // t
+    return s * span + (r - q * t) * TILE + q
+
+
+@pytest.mark.parametrize("n_tiles,tps", [(32, 32), (32, 8), (33, 8), (7, 3), (1, 1), (5, 5), (9, 2)])
+def test_sorted_slot_is_a_bijection_and_every_tile_a_strided_sample(n_tiles, tps):
+    n = n_tiles * 512
+    p = np.arange(n, dtype=np.int64)
+    sl = _sorted_slot(p, n_tiles, tps)
+    assert np.array_equal(np.sort(sl), p)                                   # every slot exactly once
+    for s0 in range(0, n_tiles, tps):                                       # a split's refs stay inside the split's tiles
+        t = min(tps, n_tiles - s0)
+        inside = (p >= s0 * 512) & (p < (s0 + t) * 512)
+        assert sl[inside].min() == s0 * 512 and sl[inside].max() == (s0 + t) * 512 - 1
+        for tile in range(s0, s0 + t):                                      # tile = every t-th position of the range, in order
+            pos = np.sort(p[(sl // 512) == tile])
+            assert np.array_equal(pos, s0 * 512 + (tile - s0) + t * np.arange(512))
+
+
+def _corner_seed(ref, q, k):
+    """search.cu grid_bbox_kernel + grid_corner_seed() in float64 (the kernel's fp32 slack is part of the formula)"""
+    eps16 = 9.6e-7
+    lo, hi = ref.min(0), ref.max(0)
+    ext = hi - lo
+    h = ext.max() / 128
+    while True:
+        dim = np.clip(np.ceil(ext / h), 1, 128).astype(np.int64)
+        if dim.prod() <= 131072:
+            break
+        h *= 2
+    cell = lambda pts, l: (np.clip(((pts - lo) / h).astype(np.int64), 0, dim - 1) >> l)
+    counts = []
+    for l in range(5):
+        d = (dim + (1 << l) - 1) >> l
+        c = cell(ref, l)
+        counts.append((np.bincount((c[:, 2] * d[1] + c[:, 1]) * d[0] + c[:, 0], minlength=int(d.prod())).reshape(d[2], d[1], d[0]), d))
+    max_w = float((np.maximum(np.abs(lo), np.abs(hi)) ** 2).sum()) * 1.000001
+    out = np.empty(len(q))
+    for i, qq in enumerate(q):
+        c0 = cell(qq[None], 0)[0]
+        lev, rho = -1, 1
+        if counts[0][0][c0[2], c0[1], c0[0]] >= k:
+            lev, rho = 0, 0
+        else:
+            for l in range(5):
+                cn, d = counts[l]
+                c = c0 >> l
+                z0, z1 = max(c[2] - 1, 0), min(c[2] + 1, d[2] - 1)
+                y0, y1 = max(c[1] - 1, 0), min(c[1] + 1, d[1] - 1)
+                x0, x1 = max(c[0] - 1, 0), min(c[0] + 1, d[0] - 1)
+                if cn[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1].sum() >= k:
+                    lev = l
+                    break
+        bound = 0.0
+        for a in range(3):
+            L, H = lo[a], hi[a]
+            if lev >= 0:
+                gl = counts[lev][1][a]
+                cl = c0[a] >> lev
+                a0, a1 = max(cl - rho, 0), min(cl + rho, gl - 1)
+                hl = h * (1 << lev)
+                L = lo[a] + a0 * hl
+                Hn = lo[a] + (a1 + 1) * hl
+                H = max(Hn, hi[a]) if a1 == gl - 1 else Hn
+            delta = 1e-3 * h + 1e-6 * max(abs(lo[a]), abs(hi[a]))
+            bound += max(abs(qq[a] - (L - delta)), abs((H + delta) - qq[a])) ** 2
+        out[i] = bound * 1.00001 + eps16 * (float((qq ** 2).sum()) + max_w) + 1e-37
+    return out
+
+
+@pytest.mark.parametrize("k", [1, 3, 16, 64])
+def test_grid_corner_threshold_bounds_the_kth_reference_distance(k):
+    """the starting threshold of the gridded top-k searches must never be below the k-th smallest distance IN THE
+    REFERENCE'S ROUNDING (all three forms) -- otherwise a true neighbour would be filtered out"""
+    a, b = synth.batch_pairs(40, 1, 6000)
+    ref, qry = a[0], b[0][:400]
+    far = (qry[:40] * 3.0 + 25.0).astype(np.float32)                        # some queries outside the refs' bounding box
+    rng = np.random.default_rng(k)
+    cl = (rng.normal(size=(3000, 3)) * 0.02 + rng.choice([-40.0, 0.0, 55.0], size=(3000, 1))).astype(np.float32)   # three tight clusters
+    for refs, qs in ((ref, qry), (ref, far), (cl, cl[::10].copy()), (ref + np.float32(2000.0), qry + np.float32(2000.0))):
+        tau0 = _corner_seed(refs.astype(np.float64), qs.astype(np.float64), k)
+        for form in (0, 1, 2):
+            _, od = strict.knn(refs[None], qs[None], k, form)
+            assert (od[0, :, k - 1].astype(np.float64) <= tau0).all(), "form %d: threshold below the k-th distance" % form
+
+
 def test_fps_oracle_is_unfused_on_the_near_tie_clouds():
     """the adversarial FPS clouds: the oracle follows the unfused arithmetic (the reference's), which differs
     from the fused one on every such cloud -- so the GPU test on the same data detects a contracted kernel"""
