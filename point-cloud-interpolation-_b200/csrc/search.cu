@@ -516,11 +516,14 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
                                                                  const GridDesc *__restrict__ desc, const unsigned *__restrict__ counts,
                                                                  const unsigned *__restrict__ cend, const float4 *__restrict__ sorted,
                                                                  float *__restrict__ seed, int exact) {
-    __shared__ __align__(16) unsigned hist_all[SEED_BINS * SEED_THREADS];   // [bin][thread]
+    // [bin][thread pair]: 16-bit counters, two threads to a word (a box is capped at SEED_MAX_REFS refs, so the low half never
+    // carries into the high one).  32-bit counters would take 224 KB per SM at 7 resident CTAs and leave the L1 28 KB: every
+    // ref load of the walk would go to L2.
+    __shared__ __align__(16) unsigned hist_all[SEED_BINS * SEED_THREADS / 2];
     const int b = blockIdx.y, qi = blockIdx.x * SEED_THREADS + threadIdx.x;
     {   // zero the histograms (16 bytes per store)
         uint4 *hz = reinterpret_cast<uint4 *>(hist_all);
-        for (int i = threadIdx.x; i < SEED_BINS * SEED_THREADS / 4; i += SEED_THREADS) hz[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < SEED_BINS * SEED_THREADS / 8; i += SEED_THREADS) hz[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     if (qi >= S) return;
@@ -556,7 +559,8 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
             const int width = hi0[0] - lo0[0];
             // bins: key = bits(d) >> 21 (8 exponent + 2 mantissa bits); the last bin but one holds the farthest corner, the last = overflow
             const int base_key = max((int)(__float_as_uint(corner) >> SEED_SHIFT) - (SEED_BINS - 2), 0);
-            unsigned *hist = hist_all + threadIdx.x;
+            unsigned *hist = hist_all + (threadIdx.x >> 1);
+            const unsigned one = (threadIdx.x & 1) ? 0x10000u : 1u, shift = (threadIdx.x & 1) * 16;
             const unsigned *ce = cend + (size_t)b * GRID_MAX_CELLS;
             const float4 *pts = sorted + (size_t)b * N;
             auto count = [&](float4 r) {
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
                 const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 int bin = (int)(__float_as_uint(d) >> SEED_SHIFT) - base_key;
                 bin = bin < 0 ? 0 : (bin > SEED_BINS - 1 ? SEED_BINS - 1 : bin);
-                atomicAdd(hist + bin * SEED_THREADS, 1u);       // result unused: a fire-and-forget RED, no read-modify-write chain
+                atomicAdd(hist + bin * (SEED_THREADS / 2), one);  // result unused: a fire-and-forget RED, no read-modify-write chain
             };
             // A dense box is one long serial walk for its thread (1100 refs at C2: 40 us for a warp on its own, the whole
             // kernel waits for it): look at every stride-th ref, ~SEED_MAX_REFS in all.  Any subset of the refs still
@@ -576,6 +580,14 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
                     const int lin0 = (z * g.dim[0][1] + y) * g.dim[0][0] + lo0[0];
                     unsigned p = lin0 > 0 ? __ldg(ce + lin0 - 1) : 0u;
                     const unsigned end = __ldg(ce + lin0 + width);
+                    // every ref is read once per warp, i.e. every load waits for L2 (~800 cycles): 16 in flight per thread
+                    for (; p + 15 * stride < end; p += 16 * stride) {
+                        float4 rr[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) rr[u] = __ldg(pts + p + u * stride);
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) count(rr[u]);
+                    }
                     for (; p + 3 * stride < end; p += 4 * stride) {
                         const float4 r0 = __ldg(pts + p), r1 = __ldg(pts + p + stride), r2 = __ldg(pts + p + 2 * stride), r3 = __ldg(pts + p + 3 * stride);
                         count(r0); count(r1); count(r2); count(r3);
@@ -585,7 +597,7 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
             unsigned cum = 0;
             int bin = 0;
             for (; bin < SEED_BINS; ++bin) {
-                cum += hist[bin * SEED_THREADS];
+                cum += (hist[bin * (SEED_THREADS / 2)] >> shift) & 0xffffu;
                 if (cum >= (unsigned)k) break;
             }
             const float e = __uint_as_float((unsigned)(base_key + bin + 1) << SEED_SHIFT);
