@@ -65,6 +65,7 @@ static void load_tuning() {
     t.drain = env_int("B200PC_DRAIN", -1);
     t.grid = env_int("B200PC_GRID", 1);
     t.seed = env_int("B200PC_SEED", 0);
+    t.debug_plan = env_int("B200PC_DEBUG_PLAN", 0);
     g_tuning = t;
     g_tuning_loaded = true;
 }

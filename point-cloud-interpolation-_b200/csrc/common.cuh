@@ -51,7 +51,8 @@ struct Tuning {
     int fps_cluster;
     int fps_flat;                            // 0: two-level arg-max (block, then cluster records); 1: flat exchange of warp keys; -1: by cluster size
     int drain;                               // search drain variant (A/B)
-    int seed;                                // 1 (default): warm start from the k-th distance inside the query's cell box; 0: from the box's farthest corner
+    int debug_plan;                          // print the plan of every streaming search to stderr
+    int seed;                                // 0 (default): starting thresholds = corner bound of the query's cell box; n > 0: k-th distance inside boxes up to level n-1
     int grid;                                // 0: top-k searches start from tau = +inf; 1: default (warm start when worth it); 2: always
 };
 const Tuning &tuning();

@@ -40,6 +40,7 @@
 #include "search.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -1317,9 +1318,14 @@ bool plan_search(int B, int N, int S, int k, int mode, SearchPlan *pl) {
                 // resident warps per SM: below ~16 the SM cannot hide the drain's latency (and below 4 it idles)
                 const double resident = fmin((double)c, (double)ctas / sms) * w;
                 const double occ = pow(fmin(1.0, resident / 16.0), 0.8);
-                // a split repeats the warm-up of the k-best list in every ref range: ~k(1+ln(n/k)) candidates each
-                const double drain = real_split * (1.0 + log(fmax(1.0, (double)N / real_split / k))) / lnk;
-                const double work = 0.5 + 0.5 * drain + (real_split > 1 ? 0.05 : 0.0);
+                // A split repeats the warm-up of the k-best list in every ref range: ~k(1+ln(n/k)) inserts each, and one
+                // insert costs about as much as filtering 130 refs (calibrated at C2, where the blind drain is half the
+                // kernel).  For k = 1 the inserts are noise next to the filter, so splitting to fill the SMs is nearly free
+                // (k=1, 65536 queries x 65536 refs: 0.97 -> 0.86 ms with 4 ranges; the former model, which weighed the
+                // drain as half the work whatever k, kept it in one range on 147 CTAs of 14 warps).
+                const double ins = 130.0 * k;
+                const double work = ((double)N + ins * real_split * (1.0 + log(fmax(1.0, (double)N / real_split / k)))) / ((double)N + ins * lnk) +
+                                    (mode == MODE_TOPK ? 0.05 * (real_split - 1) : real_split > 1 ? 0.05 : 0.0);   // merge + one more k-best warm-up per range
                 const double score = wave_eff * pad_eff * occ / work + 1e-5 * resident;
                 if (score > best_score) { best_score = score; best_q = q; best_w = w; best_split = real_split; }
             }
@@ -1384,6 +1390,10 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
         return B200PC_EWORKSPACE;
     }
     B200PC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "search: workspace must be 16-byte aligned");
+    if (tuning().debug_plan)
+        fprintf(stderr, "b200pc plan: B=%d N=%d S=%d k=%d mode=%d -> %d warps/CTA, %d queries/CTA, ref split %d (%d tiles each), grid %s, %zu B smem\n", B, N, S,
+                k, mode, pl.consumer_warps, pl.q_per_block, pl.n_split, pl.tiles_per_split,
+                pl.grid_bytes ? (pl.grid_sorted ? "sorted" : "thresholds") : "off", pl.smem_bytes);
 
     char *w = static_cast<char *>(ws);
     float4 *packed = reinterpret_cast<float4 *>(w);

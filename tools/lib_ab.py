@@ -8,6 +8,8 @@ SHAPES = [  # (kind, B, N refs, S queries, k / nsample)
     ("knn0", 32, 8192, 8192, 16), ("knn0", 1, 4096, 1024, 64), ("knn0", 1, 4096, 300, 128), ("knn0", 1, 64000, 4096, 16),
     ("knn2", 8, 16384, 16384, 1), ("knn2", 1, 65536, 65536, 1), ("knn2", 4, 8192, 8192, 1), ("knn1", 16, 4096, 16384, 3),
     ("ball", 8, 16384, 16384, 32), ("ball", 1, 16384, 1024, 16), ("ball", 1, 64000, 1024, 32), ("ball", 4, 8192, 2048, 64),
+    ("knn2", 1, 65536, 32768, 1), ("knn2", 4, 65536, 8192, 1), ("knn2", 4, 65536, 65536, 1), ("knn0", 1, 16384, 4096, 16), ("knn0", 1, 4096, 4096, 32),
+    ("knn1", 1, 1024, 16384, 3), ("knn1", 1, 4096, 16384, 3), ("ball", 1, 4096, 1024, 32), ("knn0", 4, 2048, 2048, 16), ("knn2", 2, 8192, 8192, 16),
 ]
 if len(sys.argv) > 2 and sys.argv[1] == "child":
     import numpy as np, torch
