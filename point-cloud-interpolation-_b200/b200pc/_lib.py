@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pc.so")
+# B200PC_LIBRARY=bounds loads the bounds-checked build (make bounds: the same sources with device-side index asserts) --
+# for the out-of-bounds test run only; it is slower and never the library a caller times or ships.
+LIB_PATH = os.path.join(_HERE, "libb200pc_bounds.so" if os.environ.get("B200PC_LIBRARY") == "bounds" else "libb200pc.so")
 
 OK, EINVAL, ECUDA, EWORKSPACE = 0, -1, -2, -3
 

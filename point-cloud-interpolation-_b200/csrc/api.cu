@@ -66,6 +66,7 @@ static void load_tuning() {
     t.grid = env_int("B200PC_GRID", 1);
     t.seed = env_int("B200PC_SEED", 0);
     t.debug_plan = env_int("B200PC_DEBUG_PLAN", 0);
+    t.bounds_trip = env_int("B200PC_BOUNDS_TRIP", 0);
     g_tuning = t;
     g_tuning_loaded = true;
 }
@@ -77,6 +78,8 @@ const Tuning &tuning() {
 
 // 8 independent packed-FMA chains per thread, fully register resident
 __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float *sink) {
+    // self-test of the bounds build: a negative iteration count (B200PC_BOUNDS_TRIP=1) must trap; compiled out of the shipped library
+    B200PC_DEV_ASSERT(iters >= 0);
     f32x2 a[8];
     const f32x2 m = splat2(1.0000001f), c = splat2(seed);
 #pragma unroll
@@ -128,7 +131,7 @@ extern "C" int b200pc_fma_peak(int iters, double *tflops, double *ms_out, b200pc
     B200PC_CUDA(sink.alloc(sizeof(float)));
     B200PC_CUDA(cudaEventCreate(&ev.a));
     B200PC_CUDA(cudaEventCreate(&ev.b));
-    fma_peak_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, 0.5f, static_cast<float *>(sink.p));  // warm-up
+    fma_peak_kernel<<<blocks, threads, 0, st>>>(tuning().bounds_trip ? -1 : iters / 8 + 1, 0.5f, static_cast<float *>(sink.p));  // warm-up
     B200PC_LAUNCH_CHECK();
     B200PC_CUDA(cudaEventRecord(ev.a, st));
     fma_peak_kernel<<<blocks, threads, 0, st>>>(iters, 0.5f, static_cast<float *>(sink.p));

@@ -32,6 +32,22 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define B200PC_LAUNCH_CHECK() B200PC_CUDA(cudaGetLastError())
 
+// Device-side index checks of the bounds build (make bounds, -DB200PC_BOUNDS): a violated condition prints where and traps
+// the launch, so the caller sees a CUDA error.  Compiled out of the shipped library.
+#ifdef B200PC_BOUNDS
+#include <stdio.h>
+#define B200PC_DEV_ASSERT(cond)                                                                                          \
+    do {                                                                                                                 \
+        if (!(cond)) {                                                                                                   \
+            printf("b200pc device assert failed: %s (%s:%d) block (%d,%d,%d) thread %d\n", #cond, __FILE__, __LINE__,     \
+                   (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                                  \
+            __trap();                                                                                                    \
+        }                                                                                                                \
+    } while (0)
+#else
+#define B200PC_DEV_ASSERT(cond) ((void)0)
+#endif
+
 static inline cudaStream_t as_stream(b200pc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -52,6 +68,7 @@ struct Tuning {
     int fps_flat;                            // 0: two-level arg-max (block, then cluster records); 1: flat exchange of warp keys; -1: by cluster size
     int drain;                               // search drain variant (A/B)
     int debug_plan;                          // print the plan of every streaming search to stderr
+    int bounds_trip;                         // self-test of the bounds build: b200pc_fma_peak launches with an index its check rejects
     int seed;                                // 0 (default): starting thresholds = corner bound of the query's cell box; n > 0: k-th distance inside boxes up to level n-1
     int grid;                                // 0: top-k searches start from tau = +inf; 1: default (warm start when worth it); 2: always
 };

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(FPS_T) fps_kernel(const float *__restrict__ xy
 #ifdef B200PC_FPS_TIMING
         t0 = clock64();
 #endif
+        B200PC_DEV_ASSERT(far >= 0 && far < N);
         if (rank == 0 && t == 0) out[(size_t)b * npoint + it] = far;
         if (it == npoint - 1) break;  // the last pick needs no further update
 
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(FPS_T) fps_flat_kernel(const float *__restrict
     cluster.sync();                                     // barriers initialised and copies visible everywhere
 
     for (int it = 0; it < npoint; ++it) {
+        B200PC_DEV_ASSERT(far >= 0 && far < N);
         if (rank == 0 && t == 0) out[(size_t)b * npoint + it] = far;
         if (it == npoint - 1) break;  // the last pick needs no further update
 

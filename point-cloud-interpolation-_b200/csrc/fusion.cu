@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) fusion_features_kernel(const float *__res
     const float rx = ok ? __ldg(r + 0) : qn, ry = ok ? __ldg(r + 1) : qn, rz = ok ? __ldg(r + 2) : qn;
     const float dx = __fsub_rn(rx, __ldg(q + 0)), dy = __fsub_rn(ry, __ldg(q + 1)), dz = __fsub_rn(rz, __ldg(q + 2));
     const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    B200PC_DEV_ASSERT(o >= 0 && o < plane && (!ok || (i >= 0 && i < N)));
     float *ro = resi + b * 4 * plane + o;
     __stcs(ro, dx); __stcs(ro + plane, dy); __stcs(ro + 2 * plane, dz); __stcs(ro + 3 * plane, __fsqrt_rn(n2));
     float *no = nn + b * 3 * plane + o;

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float4 *__restri
             if (i < 0) i += N;
             if (i < 0 || i >= N) { if (oob) *oob = 1; }
             else src = ((row / R) * N + i) * C4;
+            B200PC_DEV_ASSERT(src < 0 || (src >= 0 && i >= 0 && i < N));
         }
         long so[ROWS];                                   // every lane takes part in the shuffles
 #pragma unroll
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(256, interp_min_blocks(ROWS)) interp_rows_kern
         }
         if (lane < 3 * ROWS) {                          // lane = 3*u + j  ->  neighbour j of row r0+u
             const long row = r0 + lane / 3;
+            B200PC_DEV_ASSERT(i_cur >= 0 && i_cur < S);
             if (row < rows_total) src = (int)(((row / N) * S + i_cur) * C4);
         }
         int so[ROWS][3];                                 // every lane takes part in the shuffles

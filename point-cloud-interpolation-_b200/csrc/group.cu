@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) group_points_bwd_kernel(const float *__re
         __syncthreads();
         for (int sl = warp; sl < GROUP_S; sl += 8) {
             if (s0 + sl >= S || rows[sl] < 0 || rows[sl] >= N) continue;
+            B200PC_DEV_ASSERT(rows[sl] >= 0 && rows[sl] < N && d0 + dn <= D);
             float *gr = gfeat + ((size_t)b * N + rows[sl]) * D + d0;
             for (int dl = lane; dl < dn; dl += 32) atomicAdd(gr + dl, tile[sl * GROUP_BWD_STRIDE + dl]);   // RED.ADD.F32, coalesced
         }

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(GR_MAX_WARPS * 32, 1) group_async_kernel(const
                     long i = iv[u];
                     if (i < 0) i += N;
                     const int r = (i >= 0 && i < N) ? b * N + (int)i : -1;
+                    B200PC_DEV_ASSERT(sl >= 0 && sl < 32 && kk >= 0 && kk < nk && r < (b + 1) * N);
                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(ibuf + (uint32_t)sl * idx_stride + 4u * kk), "r"(r) : "memory");
                 }
             }
@@ -147,12 +148,14 @@ __global__ void __launch_bounds__(GR_MAX_WARPS * 32, 1) group_async_kernel(const
 #pragma unroll
         for (int p = 0; p < NST - 1; ++p) issue(p, p);
         int st = 0;
+        B200PC_DEV_ASSERT(b >= 0 && stile < s_tiles && k0 >= 0 && k0 < K && nk >= 1 && k0 + nk <= K);
         float *o = out + ((size_t)b * C * K + k0) * S + s;
         for (int kk = 0; kk < nk; ++kk, o += S) {
             // the xyz row (12 bytes, through the LSU) is requested BEFORE the feature rows are issued: its latency hides behind
             // the copy loop instead of stalling the warp in front of it
             const int r = row_of(lane, kk);
             const bool ok = r >= 0;
+            B200PC_DEV_ASSERT(r >= -1 && r < (b + 1) * N);
             float px = 0.0f, py = 0.0f, pz = 0.0f;
             if (live && ok) {
                 const float *xr = xyz + (size_t)r * 3;

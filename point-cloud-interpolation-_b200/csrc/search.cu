@@ -106,6 +106,7 @@ __global__ void pack_refs_kernel(const float *__restrict__ ref, int N, int n_pad
     // bank 0 (measured: 11.4 wavefronts per LDS.128 without the swizzle).  The filters take a min over the
     // whole chunk, so the order of the pairs inside a chunk does not matter to them.
     const int chunk = p >> 2, slot = (p & 3) ^ (chunk & 3);
+    B200PC_DEV_ASSERT(chunk * 4 + slot < n_pad / 2);
     float4 *o = packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2;
     o[0] = make_float4(x[0], x[1], y[0], y[1]);
     o[1] = make_float4(z[0], z[1], w[0], w[1]);
@@ -186,6 +187,7 @@ __device__ __forceinline__ int grid_cell(float v, float lo, float inv_h, int G) 
 __device__ __forceinline__ int grid_cell_index(const GridDesc &g, float x, float y, float z) {
     const int cx = grid_cell(x, g.lo[0], g.inv_h, g.dim[0][0]), cy = grid_cell(y, g.lo[1], g.inv_h, g.dim[0][1]),
               cz = grid_cell(z, g.lo[2], g.inv_h, g.dim[0][2]);
+    B200PC_DEV_ASSERT(cx >= 0 && cy >= 0 && cz >= 0 && (cz * g.dim[0][1] + cy) * g.dim[0][0] + cx < GRID_MAX_CELLS);
     return (cz * g.dim[0][1] + cy) * g.dim[0][0] + cx;
 }
 
@@ -315,8 +317,10 @@ __global__ void __launch_bounds__(256) grid_pyramid_kernel(const GridDesc *__res
         if (n == 0 || !refs) continue;
         const int cx = c % g.dim[0][0], cy = (c / g.dim[0][0]) % g.dim[0][1], cz = c / (g.dim[0][0] * g.dim[0][1]);
 #pragma unroll
-        for (int l = 1; l < GRID_LEVELS; ++l)
+        for (int l = 1; l < GRID_LEVELS; ++l) {
+            B200PC_DEV_ASSERT(g.off[l] + (((cz >> l) * g.dim[l][1] + (cy >> l)) * g.dim[l][0] + (cx >> l)) < GRID_STRIDE);
             atomicAdd(base + g.off[l] + (((cz >> l) * g.dim[l][1] + (cy >> l)) * g.dim[l][0] + (cx >> l)), n);
+        }
     }
     __shared__ unsigned sh[8];
     sum = __reduce_add_sync(0xffffffffu, sum);
@@ -369,6 +373,7 @@ __global__ void __launch_bounds__(256) grid_scan_kernel(const GridDesc *__restri
     for (int w = 0; w < warp; ++w) start += sh[w];
     uint4 o4;
     o4.x = start; o4.y = o4.x + v.x; o4.z = o4.y + v.y; o4.w = o4.z + v.z;
+    B200PC_DEV_ASSERT(c0 + 3 < GRID_MAX_CELLS);
     *reinterpret_cast<uint4 *>(out + c0) = o4;
 }
 
@@ -415,6 +420,7 @@ __device__ __forceinline__ unsigned grid_box27(const GridDesc &g, const unsigned
             for (int dx = -1; dx <= 1; ++dx) {
                 const int x = cx + dx, y = cy + dy, z = cz + dz;
                 const bool in = (unsigned)x < (unsigned)gx && (unsigned)y < (unsigned)gy && (unsigned)z < (unsigned)gz;
+                B200PC_DEV_ASSERT(!in || g.off[l] + (z * gy + y) * gx + x < GRID_STRIDE);
                 n += in ? __ldg(lv + ((size_t)z * gy + y) * gx + x) : 0u;
             }
     return n;
@@ -476,9 +482,11 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float *__restri
             w = filter_norm(torch_sq_norm(x, y, z));
             if (isfinite(x) && isfinite(y) && isfinite(z)) pos = atomicAdd(gb.cend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
             else pos = (unsigned)g.n_finite + atomicAdd(gb.tail + b, 1u);
+            B200PC_DEV_ASSERT(pos < (unsigned)N);
             if (k_seed == 0) gb.sorted[(size_t)b * N + pos] = make_float4(x, y, z, __int_as_float(i));   // only grid_seed_kernel reads it
         }
         const unsigned sl = sorted_slot(pos, n_pad / TILE, tps);
+        B200PC_DEV_ASSERT(sl < (unsigned)n_pad);
         gb.perm[(size_t)b * n_pad + sl] = i;
         const unsigned chunk = sl >> 3, slot = ((sl >> 1) & 3u) ^ (chunk & 3u);
         float *o = reinterpret_cast<float *>(packed + ((size_t)b * (n_pad / 2) + (size_t)chunk * 4 + slot) * 2) + (sl & 1u);
@@ -488,6 +496,7 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float *__restri
         const float *qp = qry + ((size_t)b * S + j) * 3;
         const float x = qp[0], y = qp[1], z = qp[2];
         const unsigned pos = atomicAdd(gb.qcend + (size_t)b * GRID_MAX_CELLS + grid_cell_index(g, x, y, z), 1u);
+        B200PC_DEV_ASSERT(pos < (unsigned)S);
         gb.qsorted[(size_t)b * S + pos] = make_float4(x, y, z, __int_as_float(j));
         if (k_seed > 0) {                                  // the query's starting threshold, here rather than in a launch of its own
             const float q[3] = {x, y, z};
@@ -580,7 +589,9 @@ __global__ void __launch_bounds__(SEED_THREADS) grid_seed_kernel(const float4 *_
                     // the cells of one x-row are neighbours in the linear order: one contiguous range of sorted refs
                     const int lin0 = (z * g.dim[0][1] + y) * g.dim[0][0] + lo0[0];
                     unsigned p = lin0 > 0 ? __ldg(ce + lin0 - 1) : 0u;
+                    B200PC_DEV_ASSERT(lin0 >= 0 && lin0 + width < GRID_MAX_CELLS);
                     const unsigned end = __ldg(ce + lin0 + width);
+                    B200PC_DEV_ASSERT(p <= end && end <= (unsigned)N);
                     // every ref is read once per warp, i.e. every load waits for L2 (~800 cycles): 16 in flight per thread
                     for (; p + 15 * stride < end; p += 16 * stride) {
                         float4 rr[16];
@@ -1001,6 +1012,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                                 int cc;
                                 if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
                                 else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+                                B200PC_DEV_ASSERT(c + cc >= 0 && c + cc < CHUNKS_PER_TILE && nc < CAND_CAP);
                                 const float4 *dp = tp + (c + cc) * REC;
                                 // logical pair p lives in pair slot p ^ (chunk & 3): lanes on different chunks spread over the banks
                                 const float4 *dq = dp + 2 * ((c + cc) & 3);
@@ -1029,6 +1041,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                             if (!__any_sync(FULL, cur != 0u)) break;
                             if (cur != 0u) {
                                 const int off = base + __ffs(cur) - 1;
+                                B200PC_DEV_ASSERT(off >= 0 && off < TILE && tile_ref0 + off < P.n_pad);
                                 cur &= cur - 1;
                                 const float d = ref_dist<FORM>(tp, off, ex, ey, ez, nq);
                                 if (d <= tau[j]) {
@@ -1036,6 +1049,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                                     // than the root's (rare; only then is the root read)
                                     const uint32_t ri = P.perm ? (uint32_t)__ldg(P.perm + (size_t)b * P.n_pad + tile_ref0 + off)
                                                                : (uint32_t)slot_to_ref(tile_ref0 + off, P.strided, P.n_pad / TILE);
+                                    B200PC_DEV_ASSERT(ri < (uint32_t)P.n_pad);
                                     if (d < tau[j] || ri < (uint32_t)lds_u64(hb)) {
                                         heap_sift_root<true>(hb, SB, (uint32_t)k * SB, ((unsigned long long)order_key(d) << 32) | ri);
                                         // never above the starting bound: the root is still the +inf sentinel until k refs are in
@@ -1057,13 +1071,17 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
                             if (m0 != 0u) { cc = __ffs(m0) - 1; m0 &= m0 - 1; }
                             else { cc = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
                             const int off0 = (c + cc) * CHUNK;
+                            B200PC_DEV_ASSERT(c + cc >= 0 && c + cc < CHUNKS_PER_TILE);
                             const float4 *dp = tp + (c + cc) * REC;
                             float d[8];
 #pragma unroll
                             for (int p = 0; p < 4; ++p) unpack2(chunk_pair_dist<FORM>(dp, c + cc, p, qcj), d[2 * p], d[2 * p + 1]);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                if (d[i] <= tau[j] && cnt[j] < k) { list[cnt[j] * QPB] = tile_ref0 + off0 + i; ++cnt[j]; }
+                                if (d[i] <= tau[j] && cnt[j] < k) {
+                                    B200PC_DEV_ASSERT(tile_ref0 + off0 + i < P.N);      // a padding record never passes the exact test
+                                    list[cnt[j] * QPB] = tile_ref0 + off0 + i; ++cnt[j];
+                                }
                             if (cnt[j] == k) {   // this query is complete: nothing can hit any more
                                 tau[j] = -CUDART_INF_F; m0 = 0u; m1 = 0u;
                                 reinterpret_cast<float *>(qrec + slot)[3] = -CUDART_INF_F;
@@ -1135,6 +1153,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
         if (qi >= P.S) continue;
         // cell-ordered queries: the result goes to the caller's row
         const size_t row = (size_t)b * P.S + (P.qsorted ? __float_as_int(__ldg(&P.qsorted[(size_t)b * P.S + qi].w)) : qi);
+        B200PC_DEV_ASSERT(row >= (size_t)b * P.S && row < (size_t)(b + 1) * P.S);
         if (P.n_split == 1) {
             int64_t *io = P.idx_out ? P.idx_out + row * k : nullptr;
             int32_t *io32 = P.idx32_out ? P.idx32_out + row * k : nullptr;
