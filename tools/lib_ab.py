@@ -36,12 +36,12 @@ if len(sys.argv) > 2 and sys.argv[1] == "child":
     print("RESULT " + json.dumps(out))
     sys.exit(0)
 res = []
-for lib in sys.argv[1:3]:
+for lib in sys.argv[1:]:
     o = subprocess.run([sys.executable, __file__, "child", lib], capture_output=True, text=True)
     line = [l for l in o.stdout.splitlines() if l.startswith("RESULT ")]
     if not line:
         print(o.stdout[-2000:], o.stderr[-2000:]); sys.exit(1)
     res.append(json.loads(line[0][7:]))
-print("%-34s %10s %10s  B/A" % ("shape", os.path.basename(sys.argv[1])[:10], os.path.basename(sys.argv[2])[:10]))
+print("%-34s " % "shape" + " ".join("%12s" % os.path.basename(a)[:12] for a in sys.argv[1:]) + "   (ratio to the first)")
 for kname in res[0]:
-    print("%-34s %10.3f %10.3f  %.3f" % (kname, res[0][kname], res[1][kname], res[1][kname] / res[0][kname]))
+    print("%-34s " % kname + " ".join("%12.3f" % r[kname] for r in res) + "   " + " ".join("%.3f" % (r[kname] / res[0][kname]) for r in res[1:]))
