@@ -220,6 +220,14 @@ int b200pc_knn_host(const float *ref, const float *qry, int B, int N, int S, int
                     float *dist);
 int b200pc_ball_query_host(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
                            int64_t *idx);
+/* Asynchronous host-buffer kNN for callers that pipeline by themselves: the H2D of ref / qry, the search and the D2H of the
+ * int32 indices (and distances, if `dist` is not null) are all enqueued on `stream`; nothing is allocated, freed or
+ * synchronised.  `arena` = caller-owned DEVICE scratch of b200pc_knn_async_host_workspace_bytes(B, N, S, k) bytes, 256-byte
+ * aligned, in use until the stream has passed the call.  With two streams and two arenas the read-back of call i overlaps
+ * the upload and search of call i+1 (what b200pc.hostio.KnnHostPipeline does above torch; host buffers should be pinned). */
+size_t b200pc_knn_async_host_workspace_bytes(int B, int N, int S, int k);
+int b200pc_knn_async_host(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx, float *dist,
+                          void *arena, size_t arena_bytes, b200pc_stream_t stream);
 int b200pc_fps_host(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *idx);
 
 #ifdef __cplusplus

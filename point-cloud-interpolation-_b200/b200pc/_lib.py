@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200pc_knn_host": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "b200pc_ball_query_host": (_i, [_p, _p, _i, _i, _i, _f, _i, _p]),
     "b200pc_fps_host": (_i, [_p, _i, _i, _i, _p, _p]),
+    "b200pc_knn_async_host_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "b200pc_knn_async_host": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
 }
 
 _lib = None

@@ -168,6 +168,49 @@ extern "C" int b200pc_knn_host(const float *ref, const float *qry, int B, int N,
     return B200PC_OK;
 }
 
+// Asynchronous host-buffer kNN: everything is enqueued on `stream` and nothing is allocated, freed or synchronised, so a
+// plain C caller can keep two calls in flight on two streams (two arenas) and overlap the read-back of one with the upload
+// and search of the next, like b200pc.hostio.KnnHostPipeline does above torch.  Host buffers should be pinned.
+static size_t knn_async_layout(int B, int N, int S, int k, size_t off[5]) {
+    const size_t sz[5] = {(size_t)B * N * 12, (size_t)B * S * 12, (size_t)B * S * k * 4, (size_t)B * S * k * 4,
+                          b200pc_search_workspace_bytes(B, N, S, k)};
+    size_t o = 0;
+    for (int i = 0; i < 5; ++i) { off[i] = o; o += align_up(sz[i], 256); }
+    return o;
+}
+
+extern "C" size_t b200pc_knn_async_host_workspace_bytes(int B, int N, int S, int k) {
+    if (B <= 0 || N <= 0 || S <= 0 || k <= 0) return 256;
+    size_t off[5];
+    return knn_async_layout(B, N, S, k, off);
+}
+
+extern "C" int b200pc_knn_async_host(const float *ref, const float *qry, int B, int N, int S, int k, int form, int32_t *idx,
+                                     float *dist, void *arena, size_t arena_bytes, b200pc_stream_t stream) {
+    B200PC_REQUIRE(ref && qry && idx && arena, "knn_async_host: null pointer");
+    B200PC_REQUIRE(B >= 1 && N >= 1 && S >= 1 && k >= 1 && k <= N, "knn_async_host: bad sizes");
+    size_t off[5];
+    const size_t need = knn_async_layout(B, N, S, k, off);
+    if (arena_bytes < need) {
+        set_error("knn_async_host: arena too small (%zu < %zu bytes)", arena_bytes, need);
+        return B200PC_EWORKSPACE;
+    }
+    B200PC_REQUIRE((reinterpret_cast<uintptr_t>(arena) & 255) == 0, "knn_async_host: the arena must be 256-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    char *a = static_cast<char *>(arena);
+    float *dref = reinterpret_cast<float *>(a + off[0]), *dq = reinterpret_cast<float *>(a + off[1]);
+    int32_t *didx = reinterpret_cast<int32_t *>(a + off[2]);
+    float *ddist = dist ? reinterpret_cast<float *>(a + off[3]) : nullptr;
+    const size_t no = (size_t)B * S * k;
+    B200PC_CUDA(cudaMemcpyAsync(dref, ref, (size_t)B * N * 12, cudaMemcpyHostToDevice, st));
+    B200PC_CUDA(cudaMemcpyAsync(dq, qry, (size_t)B * S * 12, cudaMemcpyHostToDevice, st));
+    const int rc = b200pc_knn_i32(dref, dq, B, N, S, k, form, didx, ddist, a + off[4], need - off[4], stream);
+    if (rc != B200PC_OK) return rc;
+    B200PC_CUDA(cudaMemcpyAsync(idx, didx, no * 4, cudaMemcpyDeviceToHost, st));
+    if (dist) B200PC_CUDA(cudaMemcpyAsync(dist, ddist, no * 4, cudaMemcpyDeviceToHost, st));
+    return B200PC_OK;
+}
+
 extern "C" int b200pc_ball_query_host(const float *xyz, const float *new_xyz, int B, int N, int S, float r2, int nsample,
                                       int64_t *idx) {
     B200PC_REQUIRE(xyz && new_xyz && idx, "ball_query_host: null pointer");

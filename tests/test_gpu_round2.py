@@ -223,3 +223,40 @@ def test_channel_max(cuda_dev):
     assert torch.isnan(got[3]) and torch.equal(got[[0, 1, 2, 4]], x.max(dim=1)[0][[0, 1, 2, 4]])
     y = torch.randn(5, 6, generator=g).to(cuda_dev)                     # C not a multiple of 4: served by torch
     assert torch.equal(ops.channel_max(y), y.max(dim=1)[0])
+
+
+def test_c_level_async_host_knn_pipelined_over_two_streams(cuda_dev):
+    """b200pc_knn_async_host (include/b200pc.h): a plain C caller's pipeline -- pinned host clouds in, pinned int32 indices
+    out, two streams and two device arenas, nothing synchronised inside; every step must equal the oracle."""
+    import ctypes as C
+    from b200pc import _lib
+    lib = _lib.load()
+    B, N, S, k = 2, 6000, 3000, 16
+    need = lib.b200pc_knn_async_host_workspace_bytes(B, N, S, k)
+    assert need > B * (N + S) * 12
+    streams = [torch.cuda.Stream(device=cuda_dev) for _ in range(2)]
+    arenas = [torch.empty(need, dtype=torch.uint8, device=cuda_dev) for _ in range(2)]
+    steps = []
+    for i in range(5):
+        a, b = synth.batch_pairs(60 + i, B, N)
+        ref = torch.from_numpy(a).pin_memory(); qry = torch.from_numpy(b[:, :S].copy()).pin_memory()
+        out = torch.empty(B, S, k, dtype=torch.int32).pin_memory(); dist = torch.empty(B, S, k, dtype=torch.float32).pin_memory()
+        steps.append((ref, qry, out, dist))
+    with torch.cuda.device(cuda_dev):
+        for i, (ref, qry, out, dist) in enumerate(steps):
+            st = streams[i % 2]                       # a call reuses its arena only after the previous call on ITS stream
+            rc = lib.b200pc_knn_async_host(C.c_void_p(ref.data_ptr()), C.c_void_p(qry.data_ptr()), B, N, S, k, 0,
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(dist.data_ptr()), C.c_void_p(arenas[i % 2].data_ptr()),
+                                           need, C.c_void_p(st.cuda_stream))
+            assert rc == 0, lib.b200pc_last_error()
+        for st in streams:
+            st.synchronize()
+    for ref, qry, out, dist in steps:
+        oi, od = strict.knn(ref.numpy(), qry.numpy(), k, 0)
+        np.testing.assert_array_equal(out.numpy(), oi.astype(np.int32))
+        np.testing.assert_array_equal(dist.numpy().view(np.int32), od.view(np.int32))
+    small = torch.empty(1024, dtype=torch.uint8, device=cuda_dev)
+    ref, qry, out, dist = steps[0]
+    rc = lib.b200pc_knn_async_host(C.c_void_p(ref.data_ptr()), C.c_void_p(qry.data_ptr()), B, N, S, k, 0, C.c_void_p(out.data_ptr()), None,
+                                   C.c_void_p(small.data_ptr()), 1024, None)
+    assert rc == _lib.EWORKSPACE and b"arena too small" in lib.b200pc_last_error()
