@@ -62,7 +62,7 @@ static void load_tuning() {
     t.bulk = env_int("B200PC_BULK", -1);
     t.fps_cluster = env_int("B200PC_FPS_CLUSTER", 0);
     t.fps_flat = env_int("B200PC_FPS_FLAT", -1);
-    t.drain = env_int("B200PC_DRAIN", -1);
+    t.interleave = env_int("B200PC_INTERLEAVE", 0);
     t.grid = env_int("B200PC_GRID", 1);
     t.seed = env_int("B200PC_SEED", 0);
     t.debug_plan = env_int("B200PC_DEBUG_PLAN", 0);

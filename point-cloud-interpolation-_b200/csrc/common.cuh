@@ -66,7 +66,7 @@ struct Tuning {
     int bulk;                                // 0: register-path row movers (gather.cu / group.cu) instead of rowmove.cu
     int fps_cluster;
     int fps_flat;                            // 0: two-level arg-max (block, then cluster records); 1: flat exchange of warp keys; -1: by cluster size
-    int drain;                               // search drain variant (A/B)
+    int interleave;                          // 1: cell-ordered queries are dealt out to the CTAs warp by warp instead of in contiguous blocks
     int debug_plan;                          // print the plan of every streaming search to stderr
     int bounds_trip;                         // self-test of the bounds build: b200pc_fma_peak launches with an index its check rejects
     int seed;                                // 0 (default): starting thresholds = corner bound of the query's cell box; n > 0: k-th distance inside boxes up to level n-1

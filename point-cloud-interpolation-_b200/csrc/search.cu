@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(Q == 1 ? MAX_WARPS_Q1 * 32 : MAX_WARPS * 32, Q
 
     const int ct = threadIdx.x;  // 0 .. NCT-1
     // Which query a thread owns.  Cell-ordered queries: contiguous blocks of the order by default (a CTA = a patch of space;
-    // measured 1-4 % faster on the lidar-like clouds), or dealt out warp by warp (B200PC_DRAIN=1: warp w of CTA x takes
+    // measured 1-4 % faster on the lidar-like clouds), or dealt out warp by warp (B200PC_INTERLEAVE=1: warp w of CTA x takes
     // the (w * gridDim.x + x)-th group of 32, so that no CTA holds all the sparse, loosely bounded regions).
     auto query_of = [&](int j) {
         return P.qsorted && P.interleave ? (((j * NCW + (ct >> 5)) * (int)gridDim.x + (int)blockIdx.x) << 5) + lane : (int)blockIdx.x * QPB + j * NCT + ct;
@@ -1467,7 +1467,7 @@ static int run_search(const float *ref, const float *qry, int B, int N, int S, i
     a.n_split = pl.n_split; a.tiles_per_split = pl.tiles_per_split;
     a.debug_nodrain = tn.nodrain;
     a.lane_filter = tn.filter >= 0 ? tn.filter != 0 : 1;                          // 0: A/B measurement only
-    a.qsorted = gb.qsorted; a.seed = gb.seed; a.perm = gb.perm; a.interleave = tn.drain == 1;
+    a.qsorted = gb.qsorted; a.seed = gb.seed; a.perm = gb.perm; a.interleave = tn.interleave == 1;
     a.idx_out = idx; a.idx32_out = idx32; a.dist_out = dist; a.part_d = nullptr; a.part_i = nullptr; a.part_cnt = nullptr;
     if (pl.n_split > 1) {
         const size_t rows = (size_t)B * S * pl.n_split;

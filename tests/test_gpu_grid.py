@@ -3,7 +3,7 @@
 The variants only change the ORDER in which refs and queries are visited and the threshold a query starts from; results
 must stay bit-identical to the oracle on every row.  The default only switches them on for large searches, so the knobs
 force them here on small and awkward shapes: B200PC_GRID=2 (starting thresholds only), 3 (refs and queries in cell order),
-B200PC_SEED=n (k-th distance inside the cell box up to level n-1 instead of the box's corner), B200PC_DRAIN=1 (cell-ordered
+B200PC_SEED=n (k-th distance inside the cell box up to level n-1 instead of the box's corner), B200PC_INTERLEAVE=1 (cell-ordered
 queries dealt out warp by warp)."""
 import numpy as np
 import pytest
@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 VARIANTS = [
     {"B200PC_GRID": "2"},
     {"B200PC_GRID": "3"},
-    {"B200PC_GRID": "3", "B200PC_DRAIN": "1"},
+    {"B200PC_GRID": "3", "B200PC_INTERLEAVE": "1"},
     {"B200PC_GRID": "3", "B200PC_SEED": "5"},
-    {"B200PC_GRID": "3", "B200PC_SEED": "2", "B200PC_DRAIN": "1"},
+    {"B200PC_GRID": "3", "B200PC_SEED": "2", "B200PC_INTERLEAVE": "1"},
 ]
 IDS = ["thresholds", "sorted", "sorted-interleaved", "sorted-seed5", "sorted-seed2-interleaved"]
 

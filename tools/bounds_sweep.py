@@ -13,7 +13,7 @@ ops.TUNING_AUTORELOAD = True
 
 dev = torch.device("cuda:0")
 print("library:", os.path.basename(_lib.LIB_PATH), flush=True)
-ENV = ("B200PC_GRID", "B200PC_SEED", "B200PC_DRAIN", "B200PC_SMALL_PATH", "B200PC_FORCE_SPLIT", "B200PC_BULK", "B200PC_FPS_FLAT", "B200PC_FPS_CLUSTER")
+ENV = ("B200PC_GRID", "B200PC_SEED", "B200PC_INTERLEAVE", "B200PC_SMALL_PATH", "B200PC_FORCE_SPLIT", "B200PC_BULK", "B200PC_FPS_FLAT", "B200PC_FPS_CLUSTER")
 
 
 def env(**kw):
@@ -32,7 +32,7 @@ rng = np.random.default_rng(3)
 for B, N, S, k in ((2, 3000, 700, 16), (1, 513, 31, 3), (3, 1000, 777, 1), (1, 5, 9, 5), (1, 6000, 4100, 64), (2, 16384, 1024, 8), (1, 20000, 5000, 16)):
     a, b = synth.batch_pairs(11, B, max(N, S))
     ref, qry = t(a[:, :N]), t(b[:, :S])
-    for kw in (dict(), dict(GRID=0, SMALL_PATH=0), dict(GRID=2, SMALL_PATH=0), dict(GRID=3, SMALL_PATH=0), dict(GRID=3, SMALL_PATH=0, DRAIN=1, SEED=5),
+    for kw in (dict(), dict(GRID=0, SMALL_PATH=0), dict(GRID=2, SMALL_PATH=0), dict(GRID=3, SMALL_PATH=0), dict(GRID=3, SMALL_PATH=0, INTERLEAVE=1, SEED=5),
                dict(GRID=3, SMALL_PATH=0, SEED=2, FORCE_SPLIT=3), dict(SMALL_PATH=1)):
         env(**kw)
         for form in (0, 1, 2):

@@ -34,12 +34,12 @@ def run(cases, seed, dev="cuda:0"):
       os.environ["B200PC_SMALL_PATH"] = str(int(rng.integers(0, 2)))
       # the occupancy-grid variants of the top-k search (search.cu section 1b), forced on shapes the default would run blind
       grid = rng.choice(["", "0", "2", "3", "3", "3"])
-      for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_DRAIN"): os.environ.pop(kk, None)
+      for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_INTERLEAVE"): os.environ.pop(kk, None)
       if grid:
           os.environ["B200PC_GRID"] = str(grid)
           if grid in ("2", "3"): os.environ["B200PC_SMALL_PATH"] = "0"
           if grid == "3":
-              os.environ["B200PC_SEED"] = str(rng.choice([0, 0, 2, 5])); os.environ["B200PC_DRAIN"] = str(int(rng.integers(0, 2)))
+              os.environ["B200PC_SEED"] = str(rng.choice([0, 0, 2, 5])); os.environ["B200PC_INTERLEAVE"] = str(int(rng.integers(0, 2)))
       form = int(rng.integers(0, 3)); k = int(rng.integers(1, min(N, 48) + 1))
       idx, dist = ops.knn_search(torch.from_numpy(ref).to(dev), torch.from_numpy(qry).to(dev), k, form, want_dist=True)
       oi, od = strict.knn(ref, qry, k, form)
@@ -51,8 +51,8 @@ def run(cases, seed, dev="cuda:0"):
           bad += 1
           print("MISMATCH case %d: B=%d N=%d S=%d k=%d form=%d scale=%g off=%s small=%s grid=%s seed=%s drain=%s knn_ok=%s ball_ok=%s (r=%g ns=%d)" % (
               c, B, N, S, k, form, scale, off, os.environ["B200PC_SMALL_PATH"], os.environ.get("B200PC_GRID"), os.environ.get("B200PC_SEED"),
-              os.environ.get("B200PC_DRAIN"), ok, okb, r, ns), flush=True)
-  for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_DRAIN"): os.environ.pop(kk, None)
+              os.environ.get("B200PC_INTERLEAVE"), ok, okb, r, ns), flush=True)
+  for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_INTERLEAVE"): os.environ.pop(kk, None)
   if old is None: os.environ.pop("B200PC_SMALL_PATH", None)
   else: os.environ["B200PC_SMALL_PATH"] = old
   return bad

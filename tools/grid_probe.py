@@ -1,5 +1,5 @@
 """A/B of the occupancy-grid variants of the top-k searches on the bench shapes: blind (B200PC_GRID=0), starting thresholds
-only (2), refs and queries visited in cell order as well (3; B200PC_DRAIN=1: warps dealt out over the CTAs instead of contiguous blocks) and
+only (2), refs and queries visited in cell order as well (3; B200PC_INTERLEAVE=1: warps dealt out over the CTAs instead of contiguous blocks) and
 the default choice; checks that all return identical indices.  python tools/grid_probe.py"""
 import os
 import sys
@@ -31,7 +31,7 @@ def ab(name, fn, pairs):
     outs = {}
     modes = (("blind", "0", None, None), ("thresholds", "2", None, None), ("sorted", "3", None, None), ("sorted/interleaved", "3", None, "1"), ("default", None, None, None))
     for m, g, sd, dr in modes:
-        for kk, v in (("B200PC_GRID", g), ("B200PC_SEED", sd), ("B200PC_DRAIN", dr)):
+        for kk, v in (("B200PC_GRID", g), ("B200PC_SEED", sd), ("B200PC_INTERLEAVE", dr)):
             if v is None: os.environ.pop(kk, None)
             else: os.environ[kk] = v
         ops.reload_tuning()
@@ -42,7 +42,7 @@ def ab(name, fn, pairs):
     same = all(eq(outs["blind"], outs[m[0]]) for m in modes[1:])
     print("%-46s " % name + "  ".join("%s %.3f (%.1f%%)" % (m[0], r[m[0]], pairs * 8 / r[m[0]] / 1e9 / 74.1 * 100) for m in modes)
           + "  identical=%s" % same, flush=True)
-    for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_DRAIN"): os.environ.pop(kk, None)
+    for kk in ("B200PC_GRID", "B200PC_SEED", "B200PC_INTERLEAVE"): os.environ.pop(kk, None)
     ops.reload_tuning()
 
 
